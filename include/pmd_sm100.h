@@ -1,0 +1,153 @@
+/*
+ * pmd_sm100.h -- C ABI of libpmd_sm100.so: the B200 (sm_100a) kernels behind the hot path of
+ * apasarkar/localmd (penalized / local matrix decomposition of imaging movies).
+ *
+ * The reference has no FFI of its own: its boundary is the Python API (localmd_decomposition,
+ * PMDArray).  Each entry point below replaces one jitted/XLA computation or host loop of the
+ * reference; the `replaces:` line names it as file:line under the reference checkout.  The Python
+ * host (localmd_b200/) binds these with ctypes and mirrors the reference's Python interface.
+ *
+ * Conventions (all entry points):
+ *   - every array argument is a DEVICE pointer owned by the caller (torch tensors); the library
+ *     never allocates, frees or keeps device memory and holds no global state;
+ *   - sizes are int64_t; `stream` is a cudaStream_t passed as void*; work is enqueued
+ *     asynchronously on that stream; the call is re-entrant and thread safe;
+ *   - return value: 0 ok, <0 invalid argument, >0 a cudaError_t; pmd_last_error() returns a
+ *     thread-local message for the last non-zero return on the calling thread;
+ *   - movies are frame-major: element (frame f, pixel p) at base[f*d + p], p = row*d2 + col
+ *     (the physical layout of the reference's (T,d1,d2) dataset); `dtype` selects the element type;
+ *   - "block" = one overlapping spatial tile (decomposition.py:723-739); block-local pixel index is
+ *     q = qi*bw + qj, global pixel (i0+qi)*d2 + j0+qj.
+ */
+#ifndef PMD_SM100_H
+#define PMD_SM100_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* movie element types accepted wherever a `dtype` argument appears */
+enum pmd_dtype { PMD_F32 = 0, PMD_U16 = 1, PMD_I16 = 2, PMD_U8 = 3, PMD_F64 = 4, PMD_I32 = 5 };
+
+const char* pmd_last_error(void);
+int pmd_abi_version(void);
+
+/* K1  per-pixel mean and Welch high-band noise estimate, one streaming pass.
+ * replaces: pmd_loader.py:203-291 (PMDLoader._calculate_mean_and_normalizer) and
+ *           preprocessing_utils.py:10-40 (get_mean_and_noise, get_mean_chunk, get_noise_estimate).
+ * movie: t_local frames of d pixels.  Frames are cut into chunks of 1024 starting at frame 0 of
+ * this buffer (n_chunks = ceil(t_local/1024)).  Outputs, both [n_chunks][d] float32:
+ *   mean_part[c][p]  = (sum of the chunk's frames at p) / t_total
+ *   noise_part[c][p] = Welch estimate of chunk c (0 where the chunk has < 256 frames)
+ * tab_cos / tab_sin: [128][64] float32 folded Hann-windowed DFT tables for bins 65..128
+ * (built by the host, see localmd_b200/_tables.py). */
+int pmd_stats_pass(const void* movie, int dtype, int64_t t_local, int64_t d, int64_t t_total,
+                   const float* tab_cos, const float* tab_sin, float* mean_part, float* noise_part,
+                   void* stream);
+
+/* gather + standardise frames: out[i][p] = (movie[frames[i]][p] - mean[p]) / stdv[p]  (float32).
+ * replaces: pmd_loader.py:293-298 (temporal_crop_standardized) and the first two lines of
+ *           standardize_and_filter, pmd_loader.py:374-377. */
+int pmd_standardize_frames(const void* movie, int dtype, int64_t d, const int64_t* frames, int64_t n_frames,
+                           const float* mean, const float* stdv, float* out, void* stream);
+
+/* batched Gram matrices in float64:  C[b] = A[b] A[b]^T  (or A^T A), fp32 inputs, fp64 accumulate.
+ * A[b] element (i, m) at a + b*batch_stride + i*row_stride + m*inner_stride, i < n (n <= 112),
+ * m < m_len.  C is [batch][n][n] double and must be zeroed by the caller (partial sums are added
+ * atomically).  Building block of every small orthogonalisation / SVD below.
+ * replaces: the normal-equation half of jnp.linalg.qr / jnp.linalg.svd calls at
+ *           decomposition.py:64,66,301,315,319 and pmd_loader.py:58,60. */
+int pmd_gram_f64(const float* a, int64_t batch, int64_t n, int64_t m_len, int64_t batch_stride,
+                 int64_t row_stride, int64_t inner_stride, double* c, void* stream);
+
+/* batched symmetric eigensolver (cyclic parallel Jacobi, float64, one CTA per matrix, n <= 112).
+ * c: [batch][n][n] double (destroyed).  Outputs: w [batch][n] double eigenvalues, descending;
+ * vecs [batch][n][n] float32, column j = eigenvector j, scaled per `mode`:
+ *   0: orthonormal eigenvectors E
+ *   1: E * diag(1/sqrt(w))  ("whitening": X*vecs has orthonormal columns when c = X^T X);
+ *      columns with w_j <= w_0 * 1e-24 are zeroed
+ * replaces: the small LAPACK SVD/eigh factorisations inside decomposition.py:66,301,315,319 and
+ *           pmd_loader.py:60. */
+int pmd_jacobi_eigh(double* c, int64_t batch, int64_t n, int mode, double* w, float* vecs, void* stream);
+
+/* 2x2(-ish) average pooling + temporal averaging of every block of the standardised init movie.
+ * replaces: decomposition.py:192-232 (downsample_average_pooling) + 283-290.
+ * yres: [t][d] float32.  starts: [nb][2] int32 (i0, j0).  Output bta [nb][t/taf][P] float32 with
+ * P = ceil(bh/saf)*ceil(bw/saf), pooled pixel index pi*ceil(bw/saf)+pj, XLA 'SAME' padding. */
+int pmd_block_pool_tavg(const float* yres, int64_t t, int64_t d2, int64_t d, const int32_t* starts, int64_t nb,
+                        int64_t bh, int64_t bw, int64_t saf, int64_t taf, float* bta, void* stream);
+
+/* spread a pooled spatial basis back to full resolution: w[b][q][c] = uds[b][pool(q)][c] / count(pool(q)),
+ * so that w^T * block == uds^T * pooled(block)  (decomposition.py:295-298 without materialising the
+ * pooled block).  uds: [nb][P][r], w: [nb][bh*bw][rp] (rp >= r, multiple of 4, padding zeroed). */
+int pmd_block_unpool(const float* uds, int64_t nb, int64_t bh, int64_t bw, int64_t saf, int64_t r, int64_t rp,
+                     float* w, void* stream);
+
+/* streaming block projection  out[b][c][f] = sum_q w[b][q][c] * Y_b[q][f]   (c < r, f < t).
+ * replaces: decomposition.py:295-298 (u^T * pooled block), 318 (u_final^T * block), 390-407.
+ * movie: float32 [t][d] (+ b*movie_batch_stride elements for block b: 0 = all blocks share one movie,
+ * used by the threshold simulation where every "block" is its own tiny movie).
+ * w: [nb][bh*bw][rp]; out: [nb][r][t]. */
+int pmd_block_project(const float* movie, int64_t movie_batch_stride, int64_t t, int64_t d2, int64_t d,
+                      const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* w, int64_t r,
+                      int64_t rp, float* out, void* stream);
+
+/* streaming spatial projection  s[b][q][c] = sum_f Y_b[q][f] * vb[b][c][f].
+ * replaces: decomposition.py:304-306 (block * v_basis^T).   vb: [nb][r][t]; s: [nb][bh*bw][rp]. */
+int pmd_block_spatial(const float* movie, int64_t movie_batch_stride, int64_t t, int64_t d2, int64_t d,
+                      const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* vb, int64_t r,
+                      int64_t rp, float* s, void* stream);
+
+/* roughness statistics of every component of every block + the keep-through-first-failure rule.
+ * replaces: evaluation.py:84-126 (spatial/temporal_roughness_stat), 133-192, 195-222
+ *           (filter_by_failures) and decomposition.py:502-506.
+ * u: [nb][bh*bw][rp] spatial components, v: [nb][r][t] temporal components.
+ * Outputs: sstat, tstat [nb][r] float32; ranks [nb] int32 (number of kept leading components). */
+int pmd_block_stats_rank(const float* u, const float* v, int64_t nb, int64_t bh, int64_t bw, int64_t r,
+                         int64_t rp, int64_t t, float thr_s, float thr_t, int64_t max_fail, float* sstat,
+                         float* tstat, int32_t* ranks, void* stream);
+
+/* weighted assembly of the sparse spatial matrix in block-component form.
+ * replaces: decomposition.py:811-853 (pyramid weighting, COO construction, division by the summed
+ *           weights).  For block b, kept component c (< ranks[b]) and block pixel q:
+ *   val = (1.0/cumw[pix]) * ((double)u[b][q][c] * (double)bw_img[q])        (float64, as the reference)
+ * written to uvals64[(col0[b]+c)*bpix + q]  and, as float32, to uvals32[...]. */
+int pmd_assemble_u(const float* u, int64_t nb, int64_t bh, int64_t bw, int64_t rp, const int32_t* starts,
+                   const int32_t* ranks, const int64_t* col0, const float* block_weights, const double* cumw,
+                   int64_t d2, double* uvals64, float* uvals32, void* stream);
+
+/* K7a  full-movie projection onto the local (block-supported) columns of U:
+ *   z[col0[b]+c][f] = sum_q uvals32[(col0[b]+c)*bpix+q] * (movie[f][pix(b,q)] - mean[pix]) * inv_std[pix]
+ * replaces: pmd_loader.py:316-346, 392-414 (v_projection: reshape, (Y-mu)/sigma, BCOO U^T @) for
+ *           the block columns.  mean/inv_std may be NULL (no standardisation; float32 movies only:
+ *           used for U^T (U M) in the whitening step, decomposition.py:974-981).
+ * tasks: [n_tasks][2] int32 = (block, first component) for every group of <= 4 kept components
+ * (built by the host from ranks).  z: [n_cols_total][ldz] float32, written for f < t; must be zeroed by
+ * the caller when bh*bw > 512 (pixel slabs are then accumulated atomically). */
+int pmd_project_local(const void* movie, int dtype, int64_t t, int64_t d2, int64_t d, const int32_t* starts,
+                      int64_t nb, int64_t bh, int64_t bw, const int32_t* ranks, const int64_t* col0,
+                      const int32_t* tasks, int64_t n_tasks, const float* uvals32, const float* mean,
+                      const float* inv_std, float* z, int64_t ldz, void* stream);
+
+/* K7b  full-movie projection onto dense (background) columns:
+ *   z[c][f] += sum_p basis[c][p] * (movie[f][p] - mean[p]) * inv_std[p]     (c < k <= 16)
+ * replaces: the same v_projection for the dense background columns appended at
+ *           decomposition.py:912-933.  z rows must be zeroed by the caller (atomic accumulation). */
+int pmd_project_dense(const void* movie, int dtype, int64_t t, int64_t d, const float* basis, int64_t k,
+                      const float* mean, const float* inv_std, float* z, int64_t ldz, void* stream);
+
+/* K9  frame reconstruction  out[n][i] = (sum_j U[pix[i]][j] * c[j][n]) * scale[pix[i]] + shift[pix[i]]
+ * replaces: pmdarray.py:132-171 (PMDArray.__getitem__: CSR row crop x dense temporal slice,
+ *           un-normalise, frames first).  U as CSR over physical pixel rows (float32 values, int32
+ *           column ids); c: [R][n] float32; pix: [npix] int32 physical pixel ids; scale/shift may be
+ *           NULL.  out: [n][npix] float32. */
+int pmd_reconstruct(const int64_t* indptr, const int32_t* indices, const float* values, const float* c,
+                    int64_t n, const int32_t* pix, int64_t npix, const float* scale, const float* shift,
+                    float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMD_SM100_H */

@@ -1,0 +1,251 @@
+// Small dense building blocks used by every per-block factorisation: batched Gram matrices with
+// float64 accumulation and a batched cyclic-Jacobi symmetric eigensolver in float64.
+//
+// Why float64 Gram + Jacobi instead of a float32 Householder SVD: the reference calls LAPACK-class
+// SVD/QR on r x t (50 x 5000) matrices per block (decomposition.py:64,66,301,315,319).  Forming the
+// Gram matrix squares the condition number, which in float32 would corrupt exactly the weak trailing
+// components that decide the per-block rank; products of float32 values are exact in float64, so a
+// float64 Gram followed by Jacobi (relative-accuracy stopping rule) resolves singular vectors of
+// matrices with condition numbers up to ~1e7 better than a float32 backward-stable SVD would.
+#include "common.cuh"
+
+namespace pmd {
+
+constexpr int kGramMT = 64;       // inner-dimension tile
+constexpr int kGramThreads = 256;
+constexpr int kGramMaxTiles = 7;  // ceil(56*57/2 / 256) for n <= 112
+
+// C[b] += A_b[:, m0:m1] A_b[:, m0:m1]^T, fp32 in, fp64 accumulate, 2x2 register tiles over the
+// upper triangle, atomically added into C (both triangles).
+__global__ void __launch_bounds__(kGramThreads)
+gram_f64_kernel(const float* __restrict__ a, int n, int64_t m_len, int64_t bs, int64_t rs, int64_t is,
+                int64_t m_per_cta, double* __restrict__ c) {
+    extern __shared__ double gsm[];  // [2*nt][kGramMT+1]
+    const int nt = (n + 1) / 2;
+    const int ld = kGramMT + 1;
+    const int ntiles = nt * (nt + 1) / 2;
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.y;
+    const float* ab = a + b * bs;
+    const int64_t m_begin = (int64_t)blockIdx.x * m_per_cta;
+    const int64_t m_end = min(m_len, m_begin + m_per_cta);
+
+    int ti[kGramMaxTiles], tj[kGramMaxTiles];
+    double acc[kGramMaxTiles][4];
+#pragma unroll
+    for (int k = 0; k < kGramMaxTiles; ++k) {
+        int id = tid + k * kGramThreads;
+        ti[k] = -1;
+        tj[k] = 0;
+        if (id < ntiles) {
+            int row = 0, rem = id;
+            while (rem >= nt - row) { rem -= nt - row; ++row; }
+            ti[k] = row;
+            tj[k] = row + rem;
+        }
+        acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.0;
+    }
+    // zero the padding row once (odd n)
+    if (n & 1) for (int mm = tid; mm < ld; mm += kGramThreads) gsm[(2 * nt - 1) * ld + mm] = 0.0;
+
+    for (int64_t m0 = m_begin; m0 < m_end; m0 += kGramMT) {
+        if (is == 1) {
+            for (int idx = tid; idx < n * kGramMT; idx += kGramThreads) {
+                const int i = idx / kGramMT, mm = idx % kGramMT;
+                const int64_t m = m0 + mm;
+                gsm[i * ld + mm] = m < m_end ? (double)ab[(int64_t)i * rs + m] : 0.0;
+            }
+        } else {
+            for (int idx = tid; idx < n * kGramMT; idx += kGramThreads) {
+                const int mm = idx / n, i = idx % n;
+                const int64_t m = m0 + mm;
+                gsm[i * ld + mm] = m < m_end ? (double)ab[(int64_t)i * rs + m * is] : 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kGramMaxTiles; ++k) {
+            if (ti[k] >= 0) {
+                const double* r0 = gsm + (2 * ti[k]) * ld;
+                const double* r1 = r0 + ld;
+                const double* q0 = gsm + (2 * tj[k]) * ld;
+                const double* q1 = q0 + ld;
+                double a00 = acc[k][0], a01 = acc[k][1], a10 = acc[k][2], a11 = acc[k][3];
+#pragma unroll 8
+                for (int mm = 0; mm < kGramMT; ++mm) {
+                    const double x0 = r0[mm], x1 = r1[mm], y0 = q0[mm], y1 = q1[mm];
+                    a00 = fma(x0, y0, a00);
+                    a01 = fma(x0, y1, a01);
+                    a10 = fma(x1, y0, a10);
+                    a11 = fma(x1, y1, a11);
+                }
+                acc[k][0] = a00; acc[k][1] = a01; acc[k][2] = a10; acc[k][3] = a11;
+            }
+        }
+        __syncthreads();
+    }
+    double* cb = c + b * (int64_t)n * n;
+#pragma unroll
+    for (int k = 0; k < kGramMaxTiles; ++k) {
+        if (ti[k] < 0) continue;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = 2 * ti[k] + (e >> 1), j = 2 * tj[k] + (e & 1);
+            if (i >= n || j >= n) continue;
+            atomicAdd(&cb[(int64_t)i * n + j], acc[k][e]);
+            if (ti[k] != tj[k]) atomicAdd(&cb[(int64_t)j * n + i], acc[k][e]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Batched symmetric eigensolver: parallel cyclic Jacobi (round-robin ordering), float64, one CTA per
+// matrix.  Rotations are skipped when |a_pq| <= 1e-15 sqrt(|a_pp a_qq|) (relative criterion => small
+// eigenvalues of positive definite matrices are found to high relative accuracy); the sweep loop
+// stops when a full sweep applies no rotation.
+// ------------------------------------------------------------------------------------------------
+constexpr int kJacThreads = 256;
+
+__global__ void __launch_bounds__(kJacThreads)
+jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, double* __restrict__ w_out,
+                   float* __restrict__ vec_out) {
+    extern __shared__ double jsm[];
+    const int ld = n | 1;
+    const int N = n + (n & 1);
+    const int half = N / 2;
+    double* A = jsm;                 // [n][ld]
+    double* V = A + (size_t)n * ld;  // [n][ld]
+    double* cc = V + (size_t)n * ld; // [half]
+    double* ss = cc + half;          // [half]
+    int* pp = reinterpret_cast<int*>(ss + half);  // [half]
+    int* qq = pp + half;                          // [half]
+    __shared__ int n_rot;
+    const int tid = threadIdx.x;
+    const int64_t b = blockIdx.x;
+    double* cb = cmat + b * (int64_t)n * n;
+
+    for (int idx = tid; idx < n * n; idx += kJacThreads) {
+        const int i = idx / n, j = idx % n;
+        A[i * ld + j] = cb[idx];
+        V[i * ld + j] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        if (tid == 0) n_rot = 0;
+        __syncthreads();
+        for (int step = 0; step < N - 1; ++step) {
+            if (tid < half) {
+                int p, q;
+                if (tid == 0) { p = N - 1; q = step; }
+                else { p = (step + tid) % (N - 1); q = (step - tid + (N - 1)) % (N - 1); }
+                if (p > q) { const int tmp = p; p = q; q = tmp; }
+                double c = 1.0, s = 0.0;
+                bool rot = false;
+                if (q < n) {
+                    const double apq = A[p * ld + q], app = A[p * ld + p], aqq = A[q * ld + q];
+                    if (apq != 0.0 && fabs(apq) > 1e-15 * sqrt(fabs(app * aqq))) {
+                        const double tau = (aqq - app) / (2.0 * apq);
+                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + t * t);
+                        s = t * c;
+                        rot = true;
+                    }
+                }
+                pp[tid] = rot ? p : -1;
+                qq[tid] = q;
+                cc[tid] = c;
+                ss[tid] = s;
+                if (rot) atomicAdd(&n_rot, 1);
+            }
+            __syncthreads();
+            // column rotations of A and V:  col_p <- c col_p - s col_q,  col_q <- s col_p + c col_q
+            for (int item = tid; item < half * n; item += kJacThreads) {
+                const int k = item / n, i = item % n;
+                const int p = pp[k];
+                if (p < 0) continue;
+                const int q = qq[k];
+                const double c = cc[k], s = ss[k];
+                const double aip = A[i * ld + p], aiq = A[i * ld + q];
+                A[i * ld + p] = c * aip - s * aiq;
+                A[i * ld + q] = s * aip + c * aiq;
+                const double vip = V[i * ld + p], viq = V[i * ld + q];
+                V[i * ld + p] = c * vip - s * viq;
+                V[i * ld + q] = s * vip + c * viq;
+            }
+            __syncthreads();
+            // row rotations of A
+            for (int item = tid; item < half * n; item += kJacThreads) {
+                const int k = item / n, j = item % n;
+                const int p = pp[k];
+                if (p < 0) continue;
+                const int q = qq[k];
+                const double c = cc[k], s = ss[k];
+                const double apj = A[p * ld + j], aqj = A[q * ld + j];
+                A[p * ld + j] = c * apj - s * aqj;
+                A[q * ld + j] = s * apj + c * aqj;
+            }
+            __syncthreads();
+        }
+        const int rots = n_rot;
+        __syncthreads();
+        if (rots == 0) break;
+    }
+
+    // sort descending (rank by counting), write eigenvalues and (scaled) eigenvectors
+    double* wv = cc;  // reuse: need n entries -> use A's diagonal directly instead
+    (void)wv;
+    double wmax = -1e300;
+    for (int i = 0; i < n; ++i) wmax = fmax(wmax, A[i * ld + i]);
+    for (int idx = tid; idx < n * n; idx += kJacThreads) {
+        const int r = idx / n, i = idx % n;  // element r of eigenvector i
+        const double wi = A[i * ld + i];
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const double wj = A[j * ld + j];
+            rank += (wj > wi) || (wj == wi && j < i);
+        }
+        double scale = 1.0;
+        if (mode == 1) scale = (wi > wmax * 1e-24 && wi > 0.0) ? rsqrt(wi) : 0.0;
+        vec_out[b * (int64_t)n * n + (int64_t)r * n + rank] = (float)(V[r * ld + i] * scale);
+        if (r == 0) w_out[b * (int64_t)n + rank] = wi;
+    }
+}
+
+}  // namespace pmd
+
+extern "C" int pmd_gram_f64(const float* a, int64_t batch, int64_t n, int64_t m_len, int64_t batch_stride,
+                            int64_t row_stride, int64_t inner_stride, double* c, void* stream) {
+    const char* fn = "pmd_gram_f64";
+    PMD_REQUIRE(a && c, fn, "null pointer");
+    PMD_REQUIRE(batch > 0 && batch <= 65535 && n > 0 && n <= 112 && m_len > 0, fn, "bad size (n <= 112, batch <= 65535)");
+    PMD_REQUIRE(inner_stride == 1 || row_stride == 1, fn, "one of row_stride / inner_stride must be 1");
+    // enough CTAs to fill the machine, at least 4 inner tiles each
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>((m_len + 4 * pmd::kGramMT - 1) / (4 * pmd::kGramMT),
+                                                            (4 * 148 + batch - 1) / batch));
+    int64_t m_per = (m_len + splits - 1) / splits;
+    m_per = (m_per + pmd::kGramMT - 1) / pmd::kGramMT * pmd::kGramMT;
+    splits = (m_len + m_per - 1) / m_per;
+    const int nt = (int)(n + 1) / 2;
+    const size_t smem = (size_t)2 * nt * (pmd::kGramMT + 1) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(pmd::gram_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
+    dim3 grid((unsigned)splits, (unsigned)batch);
+    pmd::gram_f64_kernel<<<grid, pmd::kGramThreads, smem, (cudaStream_t)stream>>>(a, (int)n, m_len, batch_stride, row_stride,
+                                                                                 inner_stride, m_per, c);
+    return pmd::check_launch(fn);
+}
+
+extern "C" int pmd_jacobi_eigh(double* c, int64_t batch, int64_t n, int mode, double* w, float* vecs, void* stream) {
+    const char* fn = "pmd_jacobi_eigh";
+    PMD_REQUIRE(c && w && vecs, fn, "null pointer");
+    PMD_REQUIRE(batch > 0 && n > 0 && n <= 112, fn, "bad size (n <= 112)");
+    PMD_REQUIRE(mode == 0 || mode == 1, fn, "mode must be 0 or 1");
+    const int ld = (int)n | 1;
+    const int half = ((int)n + ((int)n & 1)) / 2;
+    const size_t smem = (size_t)2 * n * ld * sizeof(double) + (size_t)2 * half * sizeof(double) + (size_t)2 * half * sizeof(int);
+    cudaError_t e = cudaFuncSetAttribute(pmd::jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
+    pmd::jacobi_eigh_kernel<<<(unsigned)batch, pmd::kJacThreads, smem, (cudaStream_t)stream>>>(c, (int)n, mode, 40, w, vecs);
+    return pmd::check_launch(fn);
+}

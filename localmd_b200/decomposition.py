@@ -1,0 +1,677 @@
+"""localmd_decomposition on one B200 (or one frame shard per GPU): the host-side mirror of the
+reference driver (decomposition.py:643-909) over the sm_100a kernels in csrc/.
+
+Same signature, defaults, guards and result object as the reference.  Extra keyword-only arguments:
+  draws      object with the reference's random quantities (same field names as the test oracle's
+             `Draws`): bg_frames, bg_sketch, init_frames, sim_noise, sim_sketch, thresholds,
+             block_sketches, prune_sketch.  Any field left None is generated on the device.
+  seed       seed for everything generated here.
+  device     CUDA device (default: current).
+  timings    dict filled with per-stage GPU milliseconds (CUDA events).
+  details    dict filled with intermediates (ranks, thresholds, background basis, ...) for tests.
+README aliases block_height/block_width/frames_to_init are accepted.
+"""
+import datetime
+import math
+import sys
+from typing import Callable, Optional
+
+import numpy as np
+import scipy.sparse
+import torch
+
+from . import ops
+from .dataset import DeviceMovie
+from .pmdarray import PMDArray
+
+
+def display(msg):
+    tag = "[" + datetime.datetime.today().strftime("%y-%m-%d %H:%M:%S") + "]: "
+    sys.stdout.write(tag + msg + "\n")
+    sys.stdout.flush()
+
+
+# ---------------------------------------------------------------------------------------------
+# host logic shared with the reference (guards, tiling, weights, window selection)
+# ---------------------------------------------------------------------------------------------
+def check_fov_size(fov_dims, min_allowed_value=10):
+    """decomposition.py:616-635."""
+    for k in fov_dims:
+        if k < min_allowed_value:
+            raise ValueError(
+                "At least one FOV dimension is lower than {}, too small to process".format(min_allowed_value)
+            )
+
+
+def update_block_sizes(blocks, fov_shape, min_block_value=10):
+    """decomposition.py:572-613."""
+    if blocks[0] < min_block_value or blocks[1] < min_block_value:
+        raise ValueError(
+            "One of the block dimensions was less than min allowed value of {}, "
+            "set to a larger value".format(min_block_value)
+        )
+    out = []
+    for b, n in zip(blocks, fov_shape):
+        if b > n:
+            display("Blocksize was set to {} but corresponding dimension has size {}. Truncating to {}".format(b, n, n))
+        out.append(min(int(b), int(n)))
+    return out
+
+
+def tile_starts(n, b):
+    """decomposition.py:698, 723-739."""
+    overlap = math.ceil(b / 2)
+    it = list(range(0, n - b + 1, b - overlap))
+    if it[-1] != n - b and n - b != 0:
+        it.append(n - b)
+    return it
+
+
+def pyramid_weights(bh, bw):
+    """decomposition.py:742-750 (even block sizes only, as in the reference)."""
+    if bh % 2 or bw % 2:
+        raise ValueError("block sizes must be even (the reference's weighting, decomposition.py:749, fails otherwise)")
+    w = np.ones((bh, bw), dtype=np.float32)
+    hbh, hbw = bh // 2, bw // 2
+    w[:hbh, :hbw] += np.minimum(np.tile(np.arange(0, hbw), (hbh, 1)), np.tile(np.arange(0, hbh), (hbw, 1)).T)
+    w[:hbh, hbw:] = np.fliplr(w[:hbh, :hbw])
+    w[hbh:, :] = np.flipud(w[:hbh, :])
+    return w
+
+
+def identify_window_chunks(frame_range, total_frames, window_chunks, rng, starting_points=None):
+    """decomposition.py:528-569."""
+    if frame_range > total_frames:
+        raise ValueError("Requested more frames than available")
+    if window_chunks > frame_range:
+        raise ValueError("The size of each temporal chunk is bigger than frame range")
+    num_intervals = math.ceil(frame_range / window_chunks)
+    available = np.arange(0, total_frames, window_chunks)
+    if available[-1] > total_frames - window_chunks:
+        available[-1] = total_frames - window_chunks
+    if starting_points is None:
+        starting_points = rng.choice(available, size=num_intervals, replace=False)
+    starting_points = np.sort(np.asarray(starting_points))
+    frames = []
+    for k in starting_points:
+        frames.extend(range(int(k), int(min(k + window_chunks, total_frames))))
+    return frames
+
+
+class _Timer:
+    def __init__(self, timings, device):
+        self.timings, self.device, self.events = timings, device, []
+
+    def mark(self, name):
+        if self.timings is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(torch.cuda.current_stream(self.device))
+        self.events.append((name, ev))
+
+    def finish(self):
+        if self.timings is None or len(self.events) < 2:
+            return
+        torch.cuda.synchronize(self.device)
+        for (_, a), (name, b) in zip(self.events[:-1], self.events[1:]):
+            self.timings[name] = self.timings.get(name, 0.0) + a.elapsed_time(b)
+
+
+def _as_dev(x, device, dtype=torch.float32):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=device, dtype=dtype).contiguous()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x))).to(device=device, dtype=dtype).contiguous()
+
+
+def sym_eigh_desc_abs(g):
+    """Eigen-decomposition of a symmetric matrix ordered by |lambda| descending -- what
+    jnp.linalg.svd(hermitian=True) returns (decomposition.py:984, 1090, 1129).  Small problems use the
+    float64 Jacobi kernel; larger ones currently go through torch.linalg.eigh (cuSOLVER).
+    Returns (|lambda| float32 (n,), vectors float32 (n,n))."""
+    n = g.shape[0]
+    if n <= 112:
+        w, vecs = ops.jacobi_eigh(g.to(torch.float64).contiguous()[None], mode=0)
+        w, vecs = w[0], vecs[0]
+    else:
+        w, vecs = torch.linalg.eigh(g)
+    order = torch.argsort(w.abs(), descending=True, stable=True)
+    return w.abs()[order].to(torch.float32), vecs[:, order].to(torch.float32).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# stage functions
+# ---------------------------------------------------------------------------------------------
+def compute_mean_and_noise(movie: DeviceMovie, compute_normalizer=True, group=None):
+    """K1 over this rank's frame shard (+ all-reduce when `group` is a process group).
+    pmd_loader.py:203-291."""
+    dev = movie.device
+    d = movie.d
+    mean = torch.zeros(d, dtype=torch.float32, device=dev)
+    noise = torch.zeros(d, dtype=torch.float32, device=dev)
+    n_var = 0
+    for _, chunk in movie.batches():
+        mp, npart, nv = ops.stats_pass(chunk, movie.T_total)
+        mean += mp.sum(dim=0)
+        noise += npart.sum(dim=0)
+        n_var += nv
+    if group is not None:
+        import torch.distributed as dist
+
+        cnt = torch.tensor([n_var], dtype=torch.int64, device=dev)
+        dist.all_reduce(mean, group=group)
+        dist.all_reduce(noise, group=group)
+        dist.all_reduce(cnt, group=group)
+        n_var = int(cnt.item())
+    flag = bool(compute_normalizer) and movie.T_total >= 256
+    if flag and n_var > 0:
+        std = noise / float(n_var)
+        std = torch.where(std == 0, torch.ones_like(std), std)
+    else:
+        std = torch.ones(d, dtype=torch.float32, device=dev)
+    return mean, std
+
+
+def background_basis(movie: DeviceMovie, mean, std, bg_frames, bg_sketch, background_rank):
+    """pmd_loader.py:300-314 + 46-68: rSVD of <= 1000 standardised frames -> (K, d) orthonormal rows."""
+    dev = movie.device
+    raw = movie.gather(bg_frames)
+    a_t = ops.standardize_frames(raw, torch.arange(raw.shape[0], device=dev), mean, std)  # (n, d) = A^T
+    y = torch.matmul(a_t.t(), bg_sketch).contiguous()  # (d, l)
+    q = ops.orthonormalize_cols(y[None])[0]  # (d, l)
+    bmat = torch.matmul(q.t(), a_t.t()).contiguous()  # (l, n)
+    _, e = ops.jacobi_eigh(ops.gram_rows(bmat[None]), mode=0)
+    u = torch.matmul(q, e[0][:, :background_rank])  # (d, K)
+    return u.t().contiguous()
+
+
+def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, chunk=50):
+    """decomposition.py:147-189: roughness statistics of the rank-1 rSVD of pure-noise blocks."""
+    b = bh * bw
+    starts = torch.zeros((chunk, 2), dtype=torch.int32, device=device)
+    sp, tp = [], []
+    have_noise = getattr(draws, "sim_noise", None) is not None
+    have_sk = getattr(draws, "sim_sketch", None) is not None
+    n_iters = len(draws.sim_noise) if have_noise else iters
+    for s0 in range(0, n_iters, chunk):
+        m = min(chunk, n_iters - s0)
+        if have_noise:
+            noise = torch.stack(
+                [_as_dev(np.asarray(draws.sim_noise[s0 + i]).transpose(2, 0, 1).reshape(t_win, b), device) for i in range(m)]
+            )
+        else:
+            noise = torch.randn((m, t_win, b), generator=gen, device=device, dtype=torch.float32)
+        if have_sk:
+            sk = torch.stack([_as_dev(draws.sim_sketch[s0 + i], device) for i in range(m)])
+        else:
+            sk = torch.randn((m, t_win, 11), generator=gen, device=device, dtype=torch.float32)
+        l = sk.shape[2]
+        y = torch.bmm(noise.transpose(1, 2), sk)  # (m, b, l)
+        q = ops.orthonormalize_cols(y)  # (m, b, l)
+        rp = (l + 3) // 4 * 4
+        qp = torch.zeros((m, b, rp), dtype=torch.float32, device=device)
+        qp[:, :, :l] = q
+        bq = ops.block_project(noise, t_win * b, t_win, bw, b, starts[:m], bh, bw, qp, l)  # (m, l, t)
+        _, e = ops.jacobi_eigh(ops.gram_rows(bq), mode=0)
+        e1 = e[:, :, :1].contiguous()  # (m, l, 1)
+        u1 = torch.zeros((m, b, 4), dtype=torch.float32, device=device)
+        u1[:, :, :1] = torch.bmm(q, e1)
+        v1 = torch.bmm(e1.transpose(1, 2), bq).contiguous()  # (m, 1, t) == s * v
+        ss, ts, _ = ops.block_stats_rank(u1, v1, bh, bw, 1, float("inf"), float("inf"), 1)
+        sp.append(ss.reshape(-1))
+        tp.append(ts.reshape(-1))
+    sp = torch.cat(sp).cpu().numpy()
+    tp = torch.cat(tp).cpu().numpy()
+    return np.percentile(sp.flatten(), sim_conf), np.percentile(tp.flatten(), sim_conf)
+
+
+def block_decompositions(yres, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_t, mcf, sketches):
+    """single_block_md (decomposition.py:235-330) for all blocks at once.
+    yres (t, d) float32, already cropped to a multiple of taf.  sketches (nb, t//taf, r+10).
+    Returns U (nb, b, rp), V (nb, r, t), ranks (nb,), sstat, tstat."""
+    dev = yres.device
+    t, d = yres.shape
+    nb = starts_dev.shape[0]
+    rp = (r + 3) // 4 * 4
+    bta = ops.block_pool_tavg(yres, d2, starts_dev, bh, bw, saf, taf)  # (nb, t', P) = B_ta^T
+    P = bta.shape[2]
+    l = sketches.shape[2]
+    if P > l:
+        y = torch.bmm(bta.transpose(1, 2), sketches)  # (nb, P, l)
+        q = ops.orthonormalize_cols(y)
+        bq = torch.bmm(q.transpose(1, 2), bta.transpose(1, 2)).contiguous()  # (nb, l, t')
+        _, e = ops.jacobi_eigh(ops.gram_rows(bq), mode=0)
+        uds = torch.bmm(q, e[:, :, :r]).contiguous()  # (nb, P, r)
+        del y, q, bq, e
+    else:
+        # reduced QR of a P x l sketch with P <= l spans R^P: the rSVD is the exact SVD of B_ta
+        if r > P:
+            raise TypeError("max_components larger than the pooled block (jax.lax.dynamic_slice would fail)")
+        c = ops.gram_f64(bta, nb, P, bta.shape[1], bta.shape[1] * P, 1, P)
+        _, e = ops.jacobi_eigh(c, mode=0)
+        uds = e[:, :, :r].contiguous()
+    del bta
+    w4 = ops.block_unpool(uds, bh, bw, saf, rp)  # (nb, b, rp)
+    vds = ops.block_project(yres, 0, t, d2, d, starts_dev, bh, bw, w4, r)  # (nb, r, t)
+    del w4
+    _, tm = ops.jacobi_eigh(ops.gram_rows(vds), mode=1)  # E diag(1/sqrt(w))
+    vb = torch.bmm(tm.transpose(1, 2), vds)  # orthonormal temporal basis (nb, r, t)
+    del vds
+    s = ops.block_spatial(yres, 0, t, d2, d, starts_dev, bh, bw, vb, rp)  # (nb, b, rp)
+    del vb
+    uf = ops.orthonormalize_cols(s, r)  # (nb, b, rp)
+    del s
+    vn = ops.block_project(yres, 0, t, d2, d, starts_dev, bh, bw, uf, r)  # (nb, r, t)
+    _, lmat = ops.jacobi_eigh(ops.gram_rows(vn), mode=0)  # (nb, r, r)
+    lpad = torch.zeros((nb, rp, rp), dtype=torch.float32, device=dev)
+    lpad[:, :r, :r] = lmat
+    u = torch.bmm(uf, lpad)  # (nb, b, rp)
+    v = torch.bmm(lmat.transpose(1, 2), vn)  # (nb, r, t)
+    del uf, vn
+    sstat, tstat, ranks = ops.block_stats_rank(u, v, bh, bw, r, thr_s, thr_t, mcf)
+    return u, v, ranks, sstat, tstat
+
+
+class SparseU:
+    """Device form of the sparse spatial matrix: block-component values + dense background rows."""
+
+    def __init__(self, starts, starts_dev, bh, bw, d1, d2, ranks_host, ranks_dev, uvals64, uvals32, bg):
+        self.starts, self.starts_dev = starts, starts_dev
+        self.bh, self.bw, self.d1, self.d2 = bh, bw, d1, d2
+        self.ranks_host, self.ranks_dev = ranks_host, ranks_dev
+        self.col0_host = np.concatenate([[0], np.cumsum(ranks_host)[:-1]]).astype(np.int64)
+        self.col0_dev = torch.from_numpy(self.col0_host).to(ranks_dev.device)
+        self.uvals64, self.uvals32 = uvals64, uvals32
+        self.bg = bg  # (K, d) float32
+        self.n_local = int(ranks_host.sum())
+        self.n_cols = self.n_local + bg.shape[0]
+        self.tasks = torch.from_numpy(ops.make_tasks(ranks_host)).to(ranks_dev.device)
+        self._csr = None
+
+    def coo_physical(self):
+        """(rows = physical pixel ids, cols, float64 values) of all stored entries, exact zeros dropped
+        (scipy's sparse product drops them at decomposition.py:853; coo_matrix(dense) at 929)."""
+        dev = self.uvals64.device
+        bpix = self.bh * self.bw
+        q = torch.arange(bpix, device=dev)
+        qi, qj = q // self.bw, q % self.bw
+        st = self.starts_dev.to(torch.int64)
+        pix_b = (st[:, 0:1] + qi[None]) * self.d2 + st[:, 1:2] + qj[None]  # (nb, bpix)
+        blk_of_col = torch.repeat_interleave(torch.arange(len(self.ranks_host), device=dev), self.ranks_dev.to(torch.int64))
+        rows = pix_b[blk_of_col].reshape(-1)
+        cols = torch.arange(self.n_local, device=dev)[:, None].expand(-1, bpix).reshape(-1)
+        vals = self.uvals64.reshape(-1)
+        K, d = self.bg.shape
+        rows = torch.cat([rows, torch.arange(d, device=dev).repeat(K)])
+        cols = torch.cat([cols, (self.n_local + torch.arange(K, device=dev))[:, None].expand(-1, d).reshape(-1)])
+        vals = torch.cat([vals, self.bg.to(torch.float64).reshape(-1)])
+        keep = vals != 0
+        return rows[keep], cols[keep], vals[keep]
+
+    def csr(self, row_ids=None):
+        """CSR arrays (indptr int64, indices int32, values float64) with rows relabelled by `row_ids`
+        (tensor mapping physical pixel -> row id; None = physical order), canonical (sorted)."""
+        rows, cols, vals = self.coo_physical()
+        if row_ids is not None:
+            rows = row_ids[rows]
+        key = rows * self.n_cols + cols
+        order = torch.argsort(key)
+        rows, cols, vals = rows[order], cols[order], vals[order]
+        d = self.d1 * self.d2
+        counts = torch.bincount(rows, minlength=d)
+        indptr = torch.zeros(d + 1, dtype=torch.int64, device=rows.device)
+        indptr[1:] = torch.cumsum(counts, 0)
+        return indptr, cols.to(torch.int32), vals
+
+    def csr_physical32(self):
+        if self._csr is None:
+            ip, ix, v = self.csr()
+            self._csr = (ip.contiguous(), ix.contiguous(), v.to(torch.float32).contiguous())
+        return self._csr
+
+    def apply(self, right):
+        """(U right)^T as an (m, d) float32 'movie' (m = right.shape[1])."""
+        ip, ix, v = self.csr_physical32()
+        d = self.d1 * self.d2
+        pix = torch.arange(d, dtype=torch.int32, device=right.device)
+        return ops.reconstruct(ip, ix, v, right.contiguous(), pix, None, None)
+
+    def project(self, movie2d, mean, inv_std, z):
+        """z[:, :n] (R, ldz) (+)= U^T standardised(movie2d)   (K7a + K7b)."""
+        n = movie2d.shape[0]
+        if self.n_local > 0:
+            if self.bh * self.bw > 512:
+                z[: self.n_local, :n].zero_()
+            ops.project_local(movie2d, self.d2, self.starts_dev, self.bh, self.bw, self.ranks_dev, self.col0_dev, self.tasks,
+                              self.uvals32, mean, inv_std, z[: self.n_local])
+        zb = z[self.n_local :]
+        zb[:, :n].zero_()
+        ops.project_dense(movie2d, self.bg, mean, inv_std, zb)
+
+
+def compute_lowrank_factorized_svd(u, v, only_left=False):
+    """decomposition.py:936-1010 on the GPU.  `u` is a SparseU (or a scipy sparse matrix, converted),
+    `v` a dense (R, t') tensor/array.  Returns the spatial mixing matrix P (R, k) (device tensor) such
+    that U P has orthonormal columns; with only_left=False also (s, Vt) of the factorised product."""
+    if not isinstance(u, SparseU):
+        u = sparse_u_from_scipy(u)
+    dev = u.uvals32.device
+    v = _as_dev(v, dev)
+    R = u.n_cols
+    right = v if R > v.shape[1] else torch.eye(R, dtype=torch.float32, device=dev)
+    m = right.shape[1]
+    wmov = u.apply(right)  # (m, d): columns of U right as frames
+    z = torch.empty((R, m), dtype=torch.float32, device=dev)
+    u.project(wmov, None, None, z)  # U^T U right
+    del wmov
+    g = torch.matmul(right.t(), z)
+    g = 0.5 * (g + g.t())
+    vals, vecs = sym_eigh_desc_abs(g)
+    good = vals > 0
+    vals, vecs = vals[good], vecs[:, good]
+    mix = torch.matmul(right, vecs) / torch.sqrt(vals)[None, :]
+    if only_left:
+        return mix
+    wmov = u.apply(v)
+    zz = torch.empty((R, v.shape[1]), dtype=torch.float32, device=dev)
+    u.project(wmov, None, None, zz)
+    new_temporal = torch.matmul(mix.t(), zz)
+    return projected_svd(mix, new_temporal)
+
+
+def sparse_u_from_scipy(u, device=None):
+    """Wrap an arbitrary scipy sparse (d, R) matrix as a SparseU made of dense columns only.  Meant for
+    the re-exported helper API on small problems, not for the main path."""
+    device = torch.device(device if device is not None else "cuda")
+    dense = torch.from_numpy(np.asarray(scipy.sparse.csr_matrix(u).todense(), dtype=np.float32)).to(device)
+    d, R = dense.shape
+    empty = np.zeros(0, dtype=np.int32)
+    return SparseU(
+        np.zeros((0, 2), np.int32), torch.zeros((0, 2), dtype=torch.int32, device=device), 2, 2, d, 1, empty.astype(np.int64),
+        torch.zeros(0, dtype=torch.int32, device=device), torch.zeros((0, 4), dtype=torch.float64, device=device),
+        torch.zeros((0, 4), dtype=torch.float32, device=device), dense.t().contiguous(),
+    )
+
+
+def projected_svd(projection, data, group=None):
+    """decomposition.py:1013-1137: Gram-based SVD of `data` (k, n) and R = projection @ left.
+    With `group`, `data` holds this rank's frame columns: the k x k Gram is all-reduced and the
+    returned Vt is the local column block."""
+    dev = data.device
+    projection = _as_dev(projection, dev)
+    k, n = data.shape
+    n_total = n
+    if group is not None:
+        import torch.distributed as dist
+
+        nt = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(nt, group=group)
+        n_total = int(nt.item())
+    if k <= n_total:
+        gram = torch.matmul(data, data.t())
+        if group is not None:
+            dist.all_reduce(gram, group=group)
+        gram = 0.5 * (gram + gram.t())
+        vals, left = sym_eigh_desc_abs(gram)
+        sing = torch.sqrt(vals)
+        div = torch.where(sing == 0, torch.ones_like(sing), sing)
+        right = torch.matmul(left.t(), data) / div[:, None]
+        return torch.matmul(projection, left), sing, right
+    if group is not None:
+        raise NotImplementedError("frame-sharded projected_svd needs k <= T")
+    gram = torch.matmul(data.t(), data)
+    gram = 0.5 * (gram + gram.t())
+    vals, right_t = sym_eigh_desc_abs(gram)
+    sing = torch.sqrt(vals)
+    div = torch.where(sing == 0, torch.ones_like(sing), sing)
+    left = torch.matmul(data, right_t / div[None, :])
+    return torch.matmul(projection, left), sing, right_t.t().contiguous()
+
+
+# ---------------------------------------------------------------------------------------------
+# driver
+# ---------------------------------------------------------------------------------------------
+def localmd_decomposition(
+    dataset_obj,
+    block_sizes=None,
+    frame_range=None,
+    max_components: int = 50,
+    background_rank: int = 15,
+    sim_conf: int = 5,
+    frame_batch_size: int = 10000,
+    dtype: str = "float32",
+    num_workers: int = 0,
+    pixel_batch_size: int = 5000,
+    max_consecutive_failures=1,
+    rank_prune: bool = False,
+    rank_prune_factor: float = 0.33,
+    temporal_avg_factor: int = 10,
+    spatial_avg_factor: int = 2,
+    order: str = "F",
+    window_chunks: Optional[int] = None,
+    compute_normalizer: bool = True,
+    pixel_weighting: Optional[np.ndarray] = None,
+    spatial_denoiser: Optional[Callable] = None,
+    temporal_denoiser: Optional[Callable] = None,
+    *,
+    block_height: Optional[int] = None,
+    block_width: Optional[int] = None,
+    frames_to_init: Optional[int] = None,
+    draws=None,
+    seed: Optional[int] = None,
+    device=None,
+    timings: Optional[dict] = None,
+    details: Optional[dict] = None,
+    verbose: bool = False,
+):
+    if block_sizes is None:
+        if block_height is None or block_width is None:
+            raise TypeError("block_sizes (or block_height and block_width) is required")
+        block_sizes = [block_height, block_width]
+    if frame_range is None:
+        if frames_to_init is None:
+            raise TypeError("frame_range (or frames_to_init) is required")
+        frame_range = frames_to_init
+    if dtype != "float32":
+        raise ValueError("only dtype='float32' is supported (the reference computes in float32 on device)")
+    if spatial_denoiser is not None or temporal_denoiser is not None:
+        raise NotImplementedError("user denoiser hooks are not implemented on the sm_100a path yet")
+    if not torch.cuda.is_available():
+        raise RuntimeError("localmd_b200 needs a CUDA device (built for sm_100a); there is no CPU fallback")
+    dev = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
+    say = display if verbose else (lambda m: None)
+
+    T, d1, d2 = (int(x) for x in dataset_obj.shape)
+    d = d1 * d2
+    check_fov_size((d1, d2))
+    rng = np.random.default_rng(seed)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(int(rng.integers(0, 2**62)))
+    draws = draws if draws is not None else object()
+    take = lambda name: getattr(draws, name, None)  # noqa: E731
+
+    with torch.cuda.device(dev):
+        tm = _Timer(timings, dev)
+        tm.mark("start")
+        movie = dataset_obj if isinstance(dataset_obj, DeviceMovie) else DeviceMovie(dataset_obj, dev, batch_frames=max(1024, frame_batch_size))
+        tm.mark("upload")
+
+        # ---- PMDLoader.__init__ : normalisers + background (pmd_loader.py:172-173) --------------
+        say("Computing Video Statistics")
+        mean, std = compute_mean_and_noise(movie, compute_normalizer)
+        inv_std = 1.0 / std
+        tm.mark("stats")
+        if background_rank > 0:
+            n_bg = min(1000, T)
+            bg_frames = take("bg_frames")
+            if bg_frames is None:
+                bg_frames = rng.choice(T, size=n_bg, replace=False).tolist()
+            bg_sketch = take("bg_sketch")
+            bg_sketch = (
+                _as_dev(bg_sketch, dev)
+                if bg_sketch is not None
+                else torch.randn((len(bg_frames), background_rank + 10), generator=gen, device=dev, dtype=torch.float32)
+            )
+            bg = background_basis(movie, mean, std, bg_frames, bg_sketch, background_rank)
+        else:
+            bg = torch.zeros((1, d), dtype=torch.float32, device=dev)
+        tm.mark("background")
+
+        # ---- frame selection (decomposition.py:678-693) ------------------------------------------
+        if window_chunks is None:
+            window_chunks = frame_range
+        if T < frame_range:
+            say("WARNING: Specified using more frames than there are in the dataset.")
+            frame_range = T
+            frames = list(range(T))
+            if frame_range <= window_chunks:
+                window_chunks = frame_range
+        else:
+            if frame_range <= window_chunks:
+                window_chunks = frame_range
+            init_frames = take("init_frames")
+            if init_frames is not None:
+                frames = [int(f) for f in init_frames]
+            else:
+                frames = identify_window_chunks(frame_range, T, window_chunks, rng)
+        if window_chunks < len(frames):
+            raise NotImplementedError("window_chunks < frame_range (residual windows) is not implemented on the sm_100a path yet")
+        say("We are initializing on a total of {} frames".format(len(frames)))
+
+        block_sizes = update_block_sizes(block_sizes, (d1, d2))
+        bh, bw = block_sizes
+
+        # ---- thresholds (decomposition.py:706-711) ------------------------------------------------
+        thr = take("thresholds")
+        if thr is not None:
+            thr_s, thr_t = float(thr[0]), float(thr[1])
+        else:
+            thr_s, thr_t = simulate_thresholds(bh, bw, window_chunks, sim_conf, draws, gen, dev)
+        tm.mark("thresholds")
+
+        # ---- init frames: standardise + background removal (pmd_loader.py:348-389) ----------------
+        raw = movie.gather(frames)
+        yres = ops.standardize_frames(raw, torch.arange(raw.shape[0], device=dev), mean, std)  # (t, d)
+        del raw
+        vbg = torch.matmul(bg, yres.t()).contiguous()  # (K, t)
+        yres.addmm_(vbg.t(), bg, alpha=-1.0)
+        if pixel_weighting is not None:
+            yres *= _as_dev(np.asarray(pixel_weighting, dtype=np.float32).reshape(-1), dev)[None, :]
+        t_init = yres.shape[0]
+        tm.mark("init_filter")
+
+        dim_1_iters, dim_2_iters = tile_starts(d1, bh), tile_starts(d2, bw)
+        starts = np.array([(k, j) for k in dim_1_iters for j in dim_2_iters], dtype=np.int32)
+        nb = starts.shape[0]
+        starts_dev = torch.from_numpy(starts).to(dev)
+        block_weights = pyramid_weights(bh, bw)
+
+        if temporal_avg_factor >= t_init:
+            raise ValueError("Need at least {} frames".format(temporal_avg_factor))
+        if t_init // temporal_avg_factor <= max_components:
+            say("WARNING: temporal avg factor is too big, max rank per block adjusted to {}.".format(t_init // temporal_avg_factor))
+            max_components = int(t_init // temporal_avg_factor)
+        crop = (t_init // temporal_avg_factor) * temporal_avg_factor
+        r = int(max_components)
+        if r + 10 > 112:
+            raise ValueError("max_components > 102 is not supported by the sm_100a Jacobi kernel")
+
+        # ---- block fits (decomposition.py:790-838) -------------------------------------------------
+        bs = take("block_sketches")
+        if bs is not None:
+            sketches = torch.stack([_as_dev(b_[0] if isinstance(b_, (list, tuple)) else b_, dev) for b_ in bs])
+        else:
+            sketches = torch.randn((nb, crop // temporal_avg_factor, r + 10), generator=gen, device=dev, dtype=torch.float32)
+        u_blk, v_blk, ranks_dev, sstat, tstat = block_decompositions(
+            yres[:crop], d2, starts_dev, bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
+            int(max_consecutive_failures), sketches,
+        )
+        del sketches
+        ranks_host = ranks_dev.cpu().numpy().astype(np.int64)
+        tm.mark("blocks")
+
+        # ---- weighted sparse assembly (decomposition.py:811-857) -----------------------------------
+        cumw = np.zeros((d1, d2), dtype=np.float64)
+        for k, j in starts:
+            cumw[k : k + bh, j : j + bw] += block_weights
+        su = _assemble(u_blk, starts, starts_dev, bh, bw, d1, d2, ranks_host, ranks_dev, block_weights, cumw, bg)
+        blk_of_col = torch.repeat_interleave(torch.arange(nb, device=dev), ranks_dev.to(torch.int64))
+        comp_of_col = torch.arange(su.n_local, device=dev) - su.col0_dev[blk_of_col]
+        v_init = torch.cat([v_blk[blk_of_col, comp_of_col], vbg[:, :crop]], dim=0)  # (R, t)
+        del u_blk, v_blk, yres
+        say("The total rank before pruning is {}".format(su.n_cols))
+        tm.mark("assemble")
+
+        # ---- orthogonalisation (decomposition.py:860-881) -------------------------------------------
+        if rank_prune:
+            if rank_prune_factor <= 0 or rank_prune_factor > 1:
+                raise ValueError("Rank prune factor should be a value in the interval (0, 1]")
+            shape = (v_init.shape[1], int(min(su.n_cols, v_init.shape[1]) * rank_prune_factor))
+            ps = take("prune_sketch")
+            if ps is not None:
+                ps = ps(shape) if callable(ps) else ps
+                ps = _as_dev(ps, dev)
+                if tuple(ps.shape) != shape:
+                    raise ValueError("prune_sketch has shape %s, expected %s" % (tuple(ps.shape), shape))
+            else:
+                ps = torch.randn(shape, generator=gen, device=dev, dtype=torch.float32)
+            p = compute_lowrank_factorized_svd(su, torch.matmul(v_init, ps), only_left=True)
+        else:
+            p = compute_lowrank_factorized_svd(su, v_init, only_left=True)
+        say("After performing rank reduction, the updated rank is {}".format(p.shape[1]))
+        tm.mark("whiten")
+
+        # ---- full-movie projection (pmd_loader.py:316-346) ------------------------------------------
+        v_full = project_movie(movie, su, p, mean, inv_std)
+        tm.mark("projection")
+
+        # ---- final SVD (decomposition.py:896-904) ---------------------------------------------------
+        rmix, s, vt = projected_svd(p, v_full)
+        good = s != 0
+        rmix, s, vt = rmix[:, good], s[good], vt[good, :]
+        tm.mark("final_svd")
+
+        # ---- result object ---------------------------------------------------------------------------
+        row_ids = torch.from_numpy(np.arange(d).reshape((d1, d2), order=order).reshape(-1)).to(dev)
+        indptr, indices, values = su.csr(row_ids)
+        u_host = scipy.sparse.csr_matrix(
+            (values.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy().astype(np.int32)), shape=(d, su.n_cols)
+        )
+        mean_img = mean.cpu().numpy().reshape(d1, d2)
+        std_img = std.cpu().numpy().reshape(d1, d2)
+        out = PMDArray(u_host, rmix.cpu().numpy(), s.cpu().numpy(), vt.cpu().numpy(), (T, d1, d2), order, mean_img, std_img, device=dev)
+        tm.mark("export")
+        tm.finish()
+        if details is not None:
+            details.update(
+                ranks=ranks_host.astype(np.int32), block_starts=[tuple(x) for x in starts.tolist()], thresholds=(thr_s, thr_t),
+                spatial_basis=np.stack([img.reshape(-1, order=order) for img in bg.cpu().numpy().reshape(-1, d1, d2)], axis=1),
+                sstat=sstat.cpu().numpy(), tstat=tstat.cpu().numpy(), mixing=p.cpu().numpy(), v_init=v_init.cpu().numpy(),
+                v_full=v_full.cpu().numpy(), frames=frames, h2d_bytes=movie.h2d_bytes,
+            )
+        return out
+
+
+def _assemble(u_blk, starts, starts_dev, bh, bw, d1, d2, ranks_host, ranks_dev, block_weights, cumw, bg):
+    dev = u_blk.device
+    col0 = torch.from_numpy(np.concatenate([[0], np.cumsum(ranks_host)[:-1]]).astype(np.int64)).to(dev)
+    n_local = int(ranks_host.sum())
+    uv64, uv32 = ops.assemble_u(
+        u_blk, bh, bw, starts_dev, ranks_dev, col0, torch.from_numpy(block_weights.reshape(-1)).to(dev),
+        torch.from_numpy(cumw.reshape(-1)).to(dev), d2, n_local,
+    )
+    return SparseU(starts, starts_dev, bh, bw, d1, d2, ranks_host, ranks_dev, uv64, uv32, bg)
+
+
+def project_movie(movie: DeviceMovie, su: SparseU, p, mean, inv_std):
+    """K7: V = P^T U^T ((Y - mean)/std) over this rank's frames -> (k, n_local) float32."""
+    dev = movie.device
+    k = p.shape[1]
+    v_full = torch.empty((k, movie.n_local), dtype=torch.float32, device=dev)
+    pt = p.t().contiguous()
+    for f0, chunk in movie.batches():
+        n = chunk.shape[0]
+        z = torch.empty((su.n_cols, n), dtype=torch.float32, device=dev)
+        su.project(chunk, mean, inv_std, z)
+        v_full[:, f0 : f0 + n].copy_(torch.matmul(pt, z))
+        del z
+    return v_full

@@ -1,0 +1,296 @@
+"""Kernel-level parity tests: every C-ABI entry point (through localmd_b200.ops -> ctypes ->
+libpmd_sm100.so) against the CPU oracle / plain NumPy float64 on seeded inputs.  Tolerances are
+written next to each comparison (float32 arithmetic with reordered sums unless stated)."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import oracle.pmd_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from localmd_b200 import ops as _ops
+
+    return _ops
+
+
+def dev(x, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    return t if dtype is None else t.to(dtype)
+
+
+# ------------------------------------------------------------------------------------------------ K1
+@pytest.mark.parametrize(
+    "T,d1,d2,dtype",
+    [(1300, 9, 13, np.float32), (2048 + 544, 8, 16, np.float32), (1024 + 176, 5, 7, np.uint16), (300, 6, 6, np.int16),
+     (200, 4, 5, np.float32), (700, 3, 70, np.uint8), (1100, 4, 4, np.float64), (2300, 4, 4, np.int32)],
+)
+def test_stats_pass(ops, T, d1, d2, dtype):
+    rng = np.random.default_rng(T + d1)
+    base = rng.uniform(50, 200, size=(d1, d2))
+    sig = rng.uniform(0.5, 4, size=(d1, d2))
+    y = base[None] + sig[None] * rng.standard_normal((T, d1, d2))
+    if np.issubdtype(dtype, np.integer):
+        y = np.clip(np.rint(y), 0, np.iinfo(dtype).max)
+    movie = y.astype(dtype)
+    mean_ref, std_ref = O.mean_and_noise(movie)
+    mp, npart, n_var = ops.stats_pass(dev(movie).view(T, d1 * d2), T)
+    mean = mp.sum(0).cpu().numpy().reshape(d1, d2)
+    np.testing.assert_allclose(mean, mean_ref, rtol=2e-6)  # float32 rounding of chunk sums
+    if T >= 256:
+        std = (npart.sum(0) / n_var).cpu().numpy().reshape(d1, d2)
+        np.testing.assert_allclose(std, std_ref, rtol=2e-5)  # fp32 DFT contraction vs scipy's float32 FFT
+    else:
+        assert n_var == 0 and float(npart.abs().max()) == 0.0
+
+
+def test_standardize_frames(ops):
+    rng = np.random.default_rng(1)
+    movie = rng.integers(0, 4000, size=(40, 37)).astype(np.uint16)
+    mean = rng.uniform(100, 200, 37).astype(np.float32)
+    std = rng.uniform(0.5, 2, 37).astype(np.float32)
+    frames = np.array([5, 0, 39, 17, 5])
+    out = ops.standardize_frames(dev(movie), dev(frames), dev(mean), dev(std)).cpu().numpy()
+    ref = (movie[frames].astype(np.float32) - mean) / std
+    np.testing.assert_array_equal(out, ref)  # same two float32 operations -> bit exact
+
+
+# ------------------------------------------------------------------------------------- gram / jacobi
+@pytest.mark.parametrize("n,m,batch", [(1, 10, 2), (2, 65, 3), (7, 700, 2), (25, 1000, 1), (50, 5000, 3), (60, 500, 2), (111, 300, 1)])
+def test_gram_and_jacobi(ops, n, m, batch):
+    rng = np.random.default_rng(n * 7 + m)
+    x = (rng.standard_normal((batch, n, m)) * np.logspace(0, -3, n)[None, :, None]).astype(np.float32)
+    g = ops.gram_rows(dev(x))
+    ref = np.einsum("bim,bjm->bij", x.astype(np.float64), x.astype(np.float64))
+    np.testing.assert_allclose(g.cpu().numpy(), ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())  # fp64 accumulation
+    gt = ops.gram_cols(dev(np.ascontiguousarray(x.transpose(0, 2, 1))))
+    np.testing.assert_allclose(gt.cpu().numpy(), ref, rtol=1e-12, atol=1e-12 * np.abs(ref).max())
+    w, vecs = ops.jacobi_eigh(g.clone(), mode=0)
+    w, vecs = w.cpu().numpy(), vecs.cpu().numpy().astype(np.float64)
+    for b in range(batch):
+        wr = np.linalg.eigvalsh(ref[b])[::-1]
+        np.testing.assert_allclose(w[b], wr, rtol=1e-9, atol=1e-13 * wr[0])
+        assert np.abs(vecs[b].T @ vecs[b] - np.eye(n)).max() < 5e-6  # float32 storage of the vectors
+        resid = ref[b] @ vecs[b] - vecs[b] * w[b][None, :]
+        assert np.abs(resid).max() < 5e-6 * wr[0]
+    _, tm = ops.jacobi_eigh(g.clone(), mode=1)
+    q = x.transpose(0, 2, 1).astype(np.float64) @ tm.cpu().numpy().astype(np.float64)
+    for b in range(batch):
+        assert np.abs(q[b].T @ q[b] - np.eye(n)).max() < 2e-4  # whitening of a kappa=1e3 matrix in one pass
+
+
+def test_orthonormalize_rank_deficient(ops):
+    rng = np.random.default_rng(5)
+    a = rng.standard_normal((2, 300, 4)).astype(np.float32)
+    x = np.concatenate([a, a[:, :, :2] * 2.0, np.zeros((2, 300, 2), np.float32)], axis=2)  # rank 4 of 8 columns
+    q = ops.orthonormalize_cols(dev(x)).cpu().numpy().astype(np.float64)
+    for b in range(2):
+        gq = q[b].T @ q[b]
+        dg = np.diag(gq)
+        assert np.all((np.abs(dg - 1) < 1e-4) | (dg < 1e-8))  # columns are orthonormal or (numerically) zero
+        live = dg > 0.5
+        assert live.sum() >= 4
+        assert np.abs(gq[np.ix_(live, live)] - np.eye(live.sum())).max() < 1e-4
+        proj = q[b][:, live] @ (q[b][:, live].T @ a[b].astype(np.float64))
+        assert np.abs(proj - a[b]).max() < 1e-4  # span contains the original columns
+
+
+# ------------------------------------------------------------------------------------ block kernels
+def _block_setup(rng, t, d1, d2, bh, bw):
+    y = rng.standard_normal((t, d1, d2)).astype(np.float32)
+    starts = np.array([(k, j) for k in O.tile_starts(d1, bh) for j in O.tile_starts(d2, bw)], dtype=np.int32)
+    return y, starts
+
+
+@pytest.mark.parametrize("bh,bw,saf,taf", [(16, 16, 2, 10), (10, 14, 2, 5), (11, 13, 2, 4), (12, 12, 3, 6), (20, 20, 2, 10)])
+def test_block_pool_tavg_and_unpool(ops, bh, bw, saf, taf):
+    rng = np.random.default_rng(bh * bw)
+    t, d1, d2 = 120, 33, 41
+    y, starts = _block_setup(rng, t, d1, d2, bh, bw)
+    bta = ops.block_pool_tavg(dev(y).view(t, -1), d2, dev(starts), bh, bw, saf, taf).cpu().numpy()
+    r = 3
+    ph, pw = -(-bh // saf), -(-bw // saf)
+    uds = rng.standard_normal((len(starts), ph * pw, r)).astype(np.float32)
+    w4 = ops.block_unpool(dev(uds), bh, bw, saf, 4).cpu().numpy()
+    for b, (i0, j0) in enumerate(starts):
+        block = y[:, i0 : i0 + bh, j0 : j0 + bw].transpose(1, 2, 0)
+        ds = O.downsample_average_pooling(block, saf)
+        ta = ds.reshape(ph * pw, t // taf, taf).mean(axis=2)  # C-order pooled pixel index, consecutive frame bins
+        np.testing.assert_allclose(bta[b].T, ta, rtol=1e-5, atol=1e-6)
+        lhs = w4[b][:, :r].T.astype(np.float64) @ block.reshape(bh * bw, t).astype(np.float64)
+        rhs = uds[b].T.astype(np.float64) @ ds.reshape(ph * pw, t).astype(np.float64)
+        np.testing.assert_allclose(lhs, rhs, atol=1e-4)
+        assert np.all(w4[b][:, r:] == 0)
+
+
+@pytest.mark.parametrize("bh,bw,r,t", [(16, 16, 8, 300), (20, 20, 50, 130), (10, 12, 5, 64), (40, 40, 13, 100)])
+def test_block_project_and_spatial(ops, bh, bw, r, t):
+    rng = np.random.default_rng(r + t)
+    d1, d2 = 47, 52
+    y, starts = _block_setup(rng, t, d1, d2, bh, bw)
+    nb = len(starts)
+    rp = (r + 3) // 4 * 4
+    w = np.zeros((nb, bh * bw, rp), np.float32)
+    w[:, :, :r] = rng.standard_normal((nb, bh * bw, r))
+    yd, sd = dev(y).view(t, -1), dev(starts)
+    out = ops.block_project(yd, 0, t, d2, d1 * d2, sd, bh, bw, dev(w), r).cpu().numpy()
+    vb = rng.standard_normal((nb, r, t)).astype(np.float32)
+    s = ops.block_spatial(yd, 0, t, d2, d1 * d2, sd, bh, bw, dev(vb), rp).cpu().numpy()
+    for b, (i0, j0) in enumerate(starts):
+        blk = y[:, i0 : i0 + bh, j0 : j0 + bw].reshape(t, bh * bw).T.astype(np.float64)  # (b, t)
+        ref = w[b][:, :r].T.astype(np.float64) @ blk
+        np.testing.assert_allclose(out[b], ref, rtol=1e-4, atol=2e-5 * np.abs(ref).max())
+        ref_s = blk @ vb[b].T.astype(np.float64)
+        np.testing.assert_allclose(s[b][:, :r], ref_s, rtol=1e-4, atol=2e-5 * np.abs(ref_s).max())
+        assert np.all(s[b][:, r:] == 0)
+
+
+def test_block_project_batched_movies(ops):
+    """movie_batch_stride != 0: every 'block' is its own small movie (threshold simulation)."""
+    rng = np.random.default_rng(0)
+    m, t, bh, bw, r = 5, 90, 12, 10, 3
+    movies = rng.standard_normal((m, t, bh * bw)).astype(np.float32)
+    w = np.zeros((m, bh * bw, 4), np.float32)
+    w[:, :, :r] = rng.standard_normal((m, bh * bw, r))
+    starts = np.zeros((m, 2), np.int32)
+    out = ops.block_project(dev(movies), t * bh * bw, t, bw, bh * bw, dev(starts), bh, bw, dev(w), r).cpu().numpy()
+    ref = np.einsum("mqc,mtq->mct", w[:, :, :r].astype(np.float64), movies.astype(np.float64))
+    np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("mcf", [1, 2, 3])
+def test_block_stats_rank(ops, mcf):
+    rng = np.random.default_rng(mcf)
+    nb, bh, bw, r, t = 7, 12, 14, 9, 257
+    rp = 12
+    ii, jj = np.mgrid[0:bh, 0:bw]
+    u = np.zeros((nb, bh * bw, rp), np.float32)
+    v = np.zeros((nb, r, t), np.float32)
+    for b in range(nb):
+        for c in range(r):
+            smooth = rng.uniform() < 0.6
+            img = np.exp(-((ii - rng.uniform(0, bh)) ** 2 + (jj - rng.uniform(0, bw)) ** 2) / 20.0) if smooth else rng.standard_normal((bh, bw))
+            tr = np.cumsum(rng.standard_normal(t)) if smooth else rng.standard_normal(t)
+            u[b, :, c] = img.reshape(-1)
+            v[b, c] = tr
+    v[3, 4] = 0.0  # NaN statistic -> failure
+    thr_s, thr_t = 0.9, 1.5
+    ss, ts, ranks = ops.block_stats_rank(dev(u), dev(v), bh, bw, r, thr_s, thr_t, mcf)
+    ss, ts, ranks = ss.cpu().numpy(), ts.cpu().numpy(), ranks.cpu().numpy()
+    for b in range(nb):
+        u3 = u[b][:, :r].reshape(bh, bw, r)
+        good, ss_ref, ts_ref = O.fitness_decisions(u3, v[b], thr_s, thr_t)
+        np.testing.assert_allclose(ss[b], ss_ref, rtol=1e-5)
+        np.testing.assert_allclose(ts[b], ts_ref, rtol=1e-5, equal_nan=True)
+        assert ranks[b] == O.filter_by_failures(good > 0, mcf).sum()
+
+
+def test_assemble_u(ops):
+    rng = np.random.default_rng(2)
+    d1, d2, bh, bw, rp = 30, 26, 12, 10, 8
+    starts = np.array([(k, j) for k in O.tile_starts(d1, bh) for j in O.tile_starts(d2, bw)], dtype=np.int32)
+    nb = len(starts)
+    u = rng.standard_normal((nb, bh * bw, rp)).astype(np.float32)
+    ranks = rng.integers(1, 7, nb).astype(np.int32)
+    col0 = np.concatenate([[0], np.cumsum(ranks)[:-1]]).astype(np.int64)
+    wts = O.pyramid_weights(bh, bw)
+    cumw = np.zeros((d1, d2))
+    for k, j in starts:
+        cumw[k : k + bh, j : j + bw] += wts
+    uv64, uv32 = ops.assemble_u(dev(u), bh, bw, dev(starts), dev(ranks), dev(col0), dev(wts.reshape(-1)), dev(cumw.reshape(-1)),
+                                d2, int(ranks.sum()))
+    uv64 = uv64.cpu().numpy()
+    for b, (i0, j0) in enumerate(starts):
+        for c in range(ranks[b]):
+            ref = (1.0 / cumw[i0 : i0 + bh, j0 : j0 + bw]) * (u[b, :, c].reshape(bh, bw).astype(np.float64) * wts.astype(np.float64))
+            np.testing.assert_array_equal(uv64[col0[b] + c].reshape(bh, bw), ref)  # same float64 operations
+    np.testing.assert_array_equal(uv32.cpu().numpy(), uv64.astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------- K7 / K9
+def _random_sparse_u(rng, d1, d2, bh, bw, max_rank, K):
+    starts = np.array([(k, j) for k in O.tile_starts(d1, bh) for j in O.tile_starts(d2, bw)], dtype=np.int32)
+    nb = len(starts)
+    ranks = rng.integers(1, max_rank + 1, nb).astype(np.int32)
+    col0 = np.concatenate([[0], np.cumsum(ranks)[:-1]]).astype(np.int64)
+    n_local = int(ranks.sum())
+    uv = rng.standard_normal((n_local, bh * bw)).astype(np.float32)
+    bg = rng.standard_normal((K, d1 * d2)).astype(np.float32)
+    rows, cols, vals = [], [], []
+    qi, qj = np.divmod(np.arange(bh * bw), bw)
+    for b, (i0, j0) in enumerate(starts):
+        pix = (i0 + qi) * d2 + j0 + qj
+        for c in range(ranks[b]):
+            rows.append(pix), cols.append(np.full(bh * bw, col0[b] + c)), vals.append(uv[col0[b] + c])
+    for k in range(K):
+        rows.append(np.arange(d1 * d2)), cols.append(np.full(d1 * d2, n_local + k)), vals.append(bg[k])
+    U = sp.csr_matrix((np.concatenate(vals).astype(np.float64), (np.concatenate(rows), np.concatenate(cols))), shape=(d1 * d2, n_local + K))
+    return starts, ranks, col0, uv, bg, U
+
+
+@pytest.mark.parametrize(
+    "bh,bw,max_rank,dtype",
+    [(10, 10, 3, np.float32), (16, 16, 9, np.uint16), (20, 20, 5, np.float32), (22, 22, 2, np.int16), (32, 32, 6, np.float32),
+     (40, 40, 3, np.uint8)],
+)
+def test_project_local_and_dense(ops, bh, bw, max_rank, dtype):
+    rng = np.random.default_rng(bh + max_rank)
+    d1, d2, T, K = 61, 83, 777, 5
+    starts, ranks, col0, uv, bg, U = _random_sparse_u(rng, d1, d2, bh, bw, max_rank, K)
+    y = rng.uniform(0, 200, size=(T, d1 * d2))
+    movie = (np.rint(y) if np.issubdtype(dtype, np.integer) else y).astype(dtype)
+    mean = rng.uniform(80, 120, d1 * d2).astype(np.float32)
+    std = rng.uniform(0.5, 2, d1 * d2).astype(np.float32)
+    inv = (1.0 / std).astype(np.float32)
+    n_local = int(ranks.sum())
+    z = torch.full((n_local + K, T + 3), 7.0, dtype=torch.float32, device="cuda")
+    if bh * bw > 512:
+        z[:n_local].zero_()
+    z[n_local:].zero_()
+    tasks = dev(ops.make_tasks(ranks))
+    ops.project_local(dev(movie), d2, dev(starts), bh, bw, dev(ranks), dev(col0), tasks, dev(uv), dev(mean), dev(inv), z[:n_local])
+    ops.project_dense(dev(movie), dev(bg), dev(mean), dev(inv), z[n_local:])
+    yc = (movie.astype(np.float64) - mean) / std
+    ref = (U.T @ yc.T)  # (R, T)
+    got = z.cpu().numpy()
+    scale = np.abs(ref).max()
+    np.testing.assert_allclose(got[:, :T], ref, rtol=0, atol=2e-5 * scale)  # float32 dot products of length <= d
+    assert np.all(got[:, T:] == np.where(np.arange(n_local + K)[:, None] < n_local, 0.0 if bh * bw > 512 else 7.0, 0.0))
+
+
+def test_project_without_standardisation(ops):
+    rng = np.random.default_rng(9)
+    d1, d2, T, K, bh, bw = 40, 36, 50, 2, 16, 16
+    starts, ranks, col0, uv, bg, U = _random_sparse_u(rng, d1, d2, bh, bw, 4, K)
+    movie = rng.standard_normal((T, d1 * d2)).astype(np.float32)
+    n_local = int(ranks.sum())
+    z = torch.zeros((n_local + K, T), dtype=torch.float32, device="cuda")
+    ops.project_local(dev(movie), d2, dev(starts), bh, bw, dev(ranks), dev(col0), dev(ops.make_tasks(ranks)), dev(uv), None, None, z[:n_local])
+    ops.project_dense(dev(movie), dev(bg), None, None, z[n_local:])
+    ref = U.T @ movie.astype(np.float64).T
+    np.testing.assert_allclose(z.cpu().numpy(), ref, atol=2e-5 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n", [1, 3, 4, 10])
+def test_reconstruct(ops, n):
+    rng = np.random.default_rng(n)
+    d1, d2 = 23, 31
+    starts, ranks, col0, uv, bg, U = _random_sparse_u(rng, d1, d2, 10, 12, 3, 2)
+    R = U.shape[1]
+    c = rng.standard_normal((R, n)).astype(np.float32)
+    pix = rng.permutation(d1 * d2)[:200].astype(np.int32)
+    scale = rng.uniform(0.5, 2, d1 * d2).astype(np.float32)
+    shift = rng.uniform(100, 200, d1 * d2).astype(np.float32)
+    U32 = U.astype(np.float32)
+    out = ops.reconstruct(dev(U32.indptr.astype(np.int64)), dev(U32.indices.astype(np.int32)), dev(U32.data), dev(c), dev(pix),
+                          dev(scale), dev(shift)).cpu().numpy()
+    ref = (U[pix] @ c.astype(np.float64)).T * scale[pix][None] + shift[pix][None]
+    np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-4)
+    out2 = ops.reconstruct(dev(U32.indptr.astype(np.int64)), dev(U32.indices.astype(np.int32)), dev(U32.data), dev(c), dev(pix),
+                           None, None).cpu().numpy()
+    np.testing.assert_allclose(out2, (U[pix] @ c.astype(np.float64)).T, rtol=1e-5, atol=1e-4)

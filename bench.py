@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- whole-job PMD compression throughput on N B200s (one process per GPU).
+
+  python bench.py --gpus N --steps K --warmup W              our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...    the reference's CPU path (NumPy/SciPy
+                                                             restatement, the JAX original cannot run here)
+
+A "step" is one full localmd_decomposition of the synthetic movie named by BASELINE.json configs[1]:
+512x512x20000 float32, 20x20 blocks, frames_to_init 5000, rank pruning on (BASELINE.md's projection
+table is quoted at k = 1650 = 0.33 * 5000).  `value` is frames/s with the movie already resident in
+HBM; `e2e` is the same call fed a HOST (pinned) numpy movie, host->device copies inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c2": dict(T=20000, d1=512, d2=512, block=20, frames_to_init=5000, n_cells=400, blob=(3.0, 5.0), bg_rank=2),
+    "c3": dict(T=20000, d1=512, d2=512, block=32, frames_to_init=5000, n_cells=400, blob=(3.0, 5.0), bg_rank=2),
+    "small": dict(T=4096, d1=128, d2=128, block=20, frames_to_init=1000, n_cells=40, blob=(3.0, 5.0), bg_rank=2),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--stage-times", action="store_true", help="print per-stage GPU ms to stderr")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_draws(T, d1, d2, block, t, r, K, rank_prune_factor, seed=0):
+    """Host-supplied random draws for the CPU baseline (thresholds are simulated by the oracle itself on a
+    reduced number of iterations to keep the baseline bounded)."""
+    import oracle.pmd_oracle as O
+
+    rng = np.random.default_rng(seed)
+    nb = len(O.tile_starts(d1, block)) * len(O.tile_starts(d2, block))
+    n_bg = min(1000, T)
+    sims = 25
+    return O.Draws(
+        bg_frames=rng.choice(T, n_bg, replace=False).tolist(),
+        bg_sketch=rng.standard_normal((n_bg, K + 10), dtype=np.float32),
+        init_frames=list(range(0, t)),
+        sim_noise=[rng.standard_normal((block, block, t), dtype=np.float32) for _ in range(sims)],
+        sim_sketch=[rng.standard_normal((t, 11), dtype=np.float32) for _ in range(sims)],
+        block_sketches=[[rng.standard_normal((t // 10, r + 10), dtype=np.float32)] for _ in range(nb)],
+        prune_sketch=lambda shape: rng.standard_normal(shape, dtype=np.float32),
+    )
+
+
+def cpu_reference_sample(w, steps=1):
+    """The reference's algorithm (NumPy/SciPy float32 restatement, oracle/pmd_oracle.py) on a bounded
+    sample of the workload: same FOV geometry class and block size, FOV 128x128, T=2048, 1024 init
+    frames.  Returns (frames/s of the sample scaled to the full workload, description, cores)."""
+    import oracle.pmd_oracle as O
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from synth import make_movie
+
+    cores = os.cpu_count() or 1
+    T, d1, d2, t = 2048, 128, 128, 1024
+    movie = make_movie(T, d1, d2, n_cells=25, seed=5, blob_sigma=w["blob"])
+    draws = oracle_draws(T, d1, d2, w["block"], t, 50, 15, 0.33)
+    best = None
+    stages = {}
+    for _ in range(steps):
+        tm = {}
+        t0 = time.perf_counter()
+        O.localmd_decomposition_oracle(movie, [w["block"], w["block"]], t, draws, rank_prune=True, timings=tm)
+        dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, stages = dt, tm
+    # scale: full-movie passes ~ pixels*T; block stage ~ blocks * t; thresholds fixed count; whitening/final ~ k^2 T
+    full_pix_T = w["d1"] * w["d2"] * w["T"]
+    s_pass = full_pix_T / (d1 * d2 * T)
+    s_blk = (w["d1"] * w["d2"] * w["frames_to_init"]) / (d1 * d2 * t)
+    est = (stages.get("stats", 0) + stages.get("projection", 0)) * s_pass + (
+        stages.get("blocks", 0) + stages.get("init_filter", 0) + stages.get("background", 0)) * s_blk + (
+        stages.get("thresholds", 0) * 10 * (w["frames_to_init"] / t)) + (stages.get("whiten", 0) + stages.get("final_svd", 0)) * s_pass
+    sample = ("restated reference (NumPy/SciPy float32, not JAX): %dx%dx%d movie, %dx%d blocks, %d init frames, rank_prune, "
+              "%.1f s measured; stage times scaled to the full workload (passes ~ pixels*T, block stage ~ blocks*t)"
+              % (d1, d2, T, w["block"], w["block"], t, best))
+    return w["T"] / est, T / best, sample, cores, stages
+
+
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = WORKLOADS[args.workload]
+    vals = []
+    for i in range(args.warmup + args.steps):
+        scaled, raw, sample, cores, stages = cpu_reference_sample(w)
+        if i >= args.warmup:
+            vals.append(scaled)
+        if i == 0 and args.warmup + args.steps > 2:
+            # one pass already costs ~10-30 s of CPU: bound the run
+            args.warmup, args.steps = min(args.warmup, 1), min(args.steps, 1)
+    v = float(np.mean(vals)) if vals else scaled
+    line = {
+        "impl": "reference", "metric": "frames/sec compressed", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * w["T"] / v, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, args.gpus),
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(name, n_gpus):
+    w = WORKLOADS[name]
+    return {"workload": "synthetic %dx%dx%d float32 two-photon movie, block %dx%d, frames_to_init %d, rank_prune 0.33 "
+                        "(BASELINE.json configs[1])" % (w["d1"], w["d2"], w["T"], w["block"], w["block"], w["frames_to_init"]),
+            "frames_per_gpu": w["T"], "timing": "inputs (21 GB/GPU) larger than L2; CUDA events, max over ranks",
+            "parallelism": "frame-sharded x%d" % n_gpus if n_gpus > 1 else "single GPU"}
+
+
+def run_ours(args):
+    import torch
+
+    import localmd_b200
+    from localmd_b200 import ops
+    from localmd_b200.synthetic import make_movie
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    T, d1, d2, blk, t_init = w["T"], w["d1"], w["d2"], w["block"], w["frames_to_init"]
+    # weak scaling: every rank compresses its own movie of the named shape (the path shards by frames with
+    # no data-path collective in this round; see DESIGN.md section "multi-GPU")
+    movie = make_movie(T, d1, d2, n_cells=w["n_cells"], blob_sigma=w["blob"], bg_rank=w["bg_rank"], seed=1234 + rank, device=dev)
+    kw = dict(block_sizes=[blk, blk], frame_range=t_init, rank_prune=True, seed=0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    stage = {"__detail__": True} if args.stage_times else {}
+    for i in range(args.warmup):
+        localmd_b200.localmd_decomposition(movie, timings=stage if (args.stage_times and i == args.warmup - 1) else None, **kw)
+    if args.stage_times and rank == 0:
+        sys.stderr.write("stage ms: %s\n" % json.dumps({k: round(v, 2) for k, v in stage.items() if isinstance(v, float)}))
+        sys.stderr.write("n_cols/ranks info: %s\n" % json.dumps(stage.get("__info__", {})))
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    n0 = ops.LAUNCHES["count"]
+    names0 = dict(ops.LAUNCHES["by_name"])
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    proj_ms = []
+    ev0.record()
+    for _ in range(args.steps):
+        tms = {}
+        localmd_b200.localmd_decomposition(movie, timings=tms, **kw)
+        proj_ms.append(tms)
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.LAUNCHES["count"] - n0
+    if world > 1:
+        tms_t = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms_t, op=dist.ReduceOp.MAX)
+        ms = float(tms_t.item())
+    ms_step = ms / args.steps
+    value = world * T / (ms_step / 1e3)
+
+    # roofline of the dominant streaming kernel pair (K7 projection pass), from the per-stage CUDA events
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    proj = float(np.mean([p["projection"] for p in proj_ms]))
+    k_final = 1650
+    alg_bytes = 4.0 * d1 * d2 * T + 4.0 * k_final * T
+    achieved = alg_bytes / (proj / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "projection pass (pmd_project_local + pmd_project_dense + mixing GEMM)",
+                "achieved": achieved, "peak": peak, "peak_source": "measured" if peaks else "fallback", "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "ms": proj}
+
+    e2e = None
+    if not args.no_e2e:
+        host = movie.cpu().numpy()
+        host_t = torch.from_numpy(host).pin_memory()
+        host_np = host_t.numpy()
+        del movie
+        torch.cuda.empty_cache()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        det = {}
+        arr = localmd_b200.localmd_decomposition(host_np, details=det, **kw)
+        frame = arr[T // 2, :, :]  # device -> host read of a reconstructed frame
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        e2e_ms = max(e0.elapsed_time(e1), wall * 1e3)
+        if world > 1:
+            tt = torch.tensor([e2e_ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_ms = float(tt.item())
+        d2h = int(arr.u.data.nbytes + arr.u.indices.nbytes + arr.u.indptr.nbytes + arr.r.nbytes + arr.s.nbytes + arr.v.nbytes
+                  + 2 * 4 * d1 * d2 + frame.nbytes)
+        e2e = {"value": world * T / (e2e_ms / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(det.get("h2d_bytes", host.nbytes)),
+               "d2h_bytes_per_step": d2h, "ms": e2e_ms}
+
+    if rank != 0:
+        return
+    line = {
+        "metric": "frames/sec compressed", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, world), "clocks": clocks,
+        "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
+        "stage_ms": {k: round(float(np.mean([p[k] for p in proj_ms])), 3) for k in proj_ms[0] if isinstance(proj_ms[0][k], float)},
+    }
+    if not args.no_cpu_baseline:
+        scaled, raw, sample, cores, _ = cpu_reference_sample(w)
+        line["cpu_baseline"] = {"value": scaled, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                                "sample_frames_per_s": raw}
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

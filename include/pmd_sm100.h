@@ -147,6 +147,17 @@ int pmd_reconstruct(const int64_t* indptr, const int32_t* indices, const float* 
                     int64_t n, const int32_t* pix, int64_t npix, const float* scale, const float* shift,
                     float* out, void* stream);
 
+/* float64 variants for the whitening step  G = M^T (U^T U) M  (decomposition.py:974-996): the Gram
+ * matrix of the denoised init movie spans > 8 decades, so U M and U^T (U M) are formed in float64.
+ * pmd_reconstruct_f64: out[n][i] = sum_j U[pix[i]][j] c[j][n]        (CSR float64 values, c [R][n] float64)
+ * pmd_project_cols_f64: z[col][f] = sum_p U[p][col] w[f][p]          (w [m][d] float64; local columns from
+ *   uvals64 [n_local][bh*bw] via blk_of_col/starts, then n_cols-n_local dense rows bg64 [.][d]); z [n_cols][m]. */
+int pmd_reconstruct_f64(const int64_t* indptr, const int32_t* indices, const double* values, const double* c,
+                        int64_t n, const int32_t* pix, int64_t npix, double* out, void* stream);
+int pmd_project_cols_f64(const double* w, int64_t m, int64_t d2, int64_t d, const int32_t* starts, int64_t bh,
+                         int64_t bw, const int32_t* blk_of_col, const int64_t* col0, int64_t n_local,
+                         const double* uvals64, const double* bg64, int64_t n_cols, double* z, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

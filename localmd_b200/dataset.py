@@ -168,6 +168,10 @@ class DeviceMovie:
     def n_local(self):
         return self.hi - self.lo
 
+    @property
+    def shape(self):
+        return (self.T_total, self.d1, self.d2)
+
     def _host_frames(self, ids):
         arr = np.asarray(self._src[list(ids)])
         if arr.ndim == 2:

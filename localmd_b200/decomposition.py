@@ -98,9 +98,19 @@ def identify_window_chunks(frame_range, total_frames, window_chunks, rng, starti
     return frames
 
 
+_ACTIVE_TIMER = None
+
+
+def _submark(name):
+    """Sub-stage CUDA-event mark (only when the caller asked for timings with detail)."""
+    if _ACTIVE_TIMER is not None and _ACTIVE_TIMER.detail:
+        _ACTIVE_TIMER.mark(name)
+
+
 class _Timer:
     def __init__(self, timings, device):
         self.timings, self.device, self.events = timings, device, []
+        self.detail = bool(timings is not None and timings.get("__detail__", False))
 
     def mark(self, name):
         if self.timings is None:
@@ -114,7 +124,11 @@ class _Timer:
             return
         torch.cuda.synchronize(self.device)
         for (_, a), (name, b) in zip(self.events[:-1], self.events[1:]):
-            self.timings[name] = self.timings.get(name, 0.0) + a.elapsed_time(b)
+            dt = a.elapsed_time(b)
+            self.timings[name] = self.timings.get(name, 0.0) + dt
+            if self.detail and "." in name:  # sub-stage marks also count towards their stage
+                top = name.split(".")[0]
+                self.timings[top] = self.timings.get(top, 0.0) + dt
 
 
 def _as_dev(x, device, dtype=torch.float32):
@@ -125,17 +139,18 @@ def _as_dev(x, device, dtype=torch.float32):
 
 def sym_eigh_desc_abs(g):
     """Eigen-decomposition of a symmetric matrix ordered by |lambda| descending -- what
-    jnp.linalg.svd(hermitian=True) returns (decomposition.py:984, 1090, 1129).  Small problems use the
-    float64 Jacobi kernel; larger ones currently go through torch.linalg.eigh (cuSOLVER).
-    Returns (|lambda| float32 (n,), vectors float32 (n,n))."""
+    jnp.linalg.svd(hermitian=True) returns (decomposition.py:984, 1090, 1129) -- in float64.
+    Small problems use the Jacobi kernel; larger ones currently go through torch.linalg.eigh (cuSOLVER).
+    Returns (|lambda| float64 (n,), vectors float64 (n,n))."""
     n = g.shape[0]
+    g = g.to(torch.float64)
     if n <= 112:
-        w, vecs = ops.jacobi_eigh(g.to(torch.float64).contiguous()[None], mode=0)
-        w, vecs = w[0], vecs[0]
+        w, vecs = ops.jacobi_eigh(g.contiguous().clone()[None], mode=0)
+        w, vecs = w[0], vecs[0].to(torch.float64)
     else:
         w, vecs = torch.linalg.eigh(g)
     order = torch.argsort(w.abs(), descending=True, stable=True)
-    return w.abs()[order].to(torch.float32), vecs[:, order].to(torch.float32).contiguous()
+    return w.abs()[order], vecs[:, order].contiguous()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -233,6 +248,7 @@ def block_decompositions(yres, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_t
     nb = starts_dev.shape[0]
     rp = (r + 3) // 4 * 4
     bta = ops.block_pool_tavg(yres, d2, starts_dev, bh, bw, saf, taf)  # (nb, t', P) = B_ta^T
+    _submark("blocks.pool")
     P = bta.shape[2]
     l = sketches.shape[2]
     if P > l:
@@ -250,24 +266,38 @@ def block_decompositions(yres, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_t
         _, e = ops.jacobi_eigh(c, mode=0)
         uds = e[:, :, :r].contiguous()
     del bta
+    _submark("blocks.rsvd")
     w4 = ops.block_unpool(uds, bh, bw, saf, rp)  # (nb, b, rp)
     vds = ops.block_project(yres, 0, t, d2, d, starts_dev, bh, bw, w4, r)  # (nb, r, t)
     del w4
-    _, tm = ops.jacobi_eigh(ops.gram_rows(vds), mode=1)  # E diag(1/sqrt(w))
+    _submark("blocks.project1")
+    g4 = ops.gram_rows(vds)
+    _submark("blocks.gram1")
+    _, tm = ops.jacobi_eigh(g4, mode=1)  # E diag(1/sqrt(w))
+    _submark("blocks.jacobi1")
     vb = torch.bmm(tm.transpose(1, 2), vds)  # orthonormal temporal basis (nb, r, t)
     del vds
+    _submark("blocks.bmm_vb")
     s = ops.block_spatial(yres, 0, t, d2, d, starts_dev, bh, bw, vb, rp)  # (nb, b, rp)
     del vb
+    _submark("blocks.spatial")
     uf = ops.orthonormalize_cols(s, r)  # (nb, b, rp)
     del s
+    _submark("blocks.orth_s")
     vn = ops.block_project(yres, 0, t, d2, d, starts_dev, bh, bw, uf, r)  # (nb, r, t)
-    _, lmat = ops.jacobi_eigh(ops.gram_rows(vn), mode=0)  # (nb, r, r)
+    _submark("blocks.project2")
+    g6 = ops.gram_rows(vn)
+    _submark("blocks.gram2")
+    _, lmat = ops.jacobi_eigh(g6, mode=0)  # (nb, r, r)
+    _submark("blocks.jacobi2")
     lpad = torch.zeros((nb, rp, rp), dtype=torch.float32, device=dev)
     lpad[:, :r, :r] = lmat
     u = torch.bmm(uf, lpad)  # (nb, b, rp)
     v = torch.bmm(lmat.transpose(1, 2), vn)  # (nb, r, t)
     del uf, vn
+    _submark("blocks.bmm_uv")
     sstat, tstat, ranks = ops.block_stats_rank(u, v, bh, bw, r, thr_s, thr_t, mcf)
+    _submark("blocks.stats")
     return u, v, ranks, sstat, tstat
 
 
@@ -322,6 +352,21 @@ class SparseU:
         indptr[1:] = torch.cumsum(counts, 0)
         return indptr, cols.to(torch.int32), vals
 
+    def utu_times_f64(self, right64):
+        """U^T U right in float64 (the two sparse products of decomposition.py:974-981)."""
+        if getattr(self, "_csr64", None) is None:
+            ip, ix, v = self.csr()
+            self._csr64 = (ip.contiguous(), ix.contiguous(), v.contiguous())
+            self._blk_of_col = torch.repeat_interleave(
+                torch.arange(len(self.ranks_host), device=v.device, dtype=torch.int32), self.ranks_dev.to(torch.int64)
+            ).contiguous()
+        ip, ix, v = self._csr64
+        d = self.d1 * self.d2
+        pix = torch.arange(d, dtype=torch.int32, device=right64.device)
+        w = ops.reconstruct_f64(ip, ix, v, right64.contiguous(), pix)  # (m, d): columns of U right as frames
+        return ops.project_cols_f64(w, self.d2, self.starts_dev, self.bh, self.bw, self._blk_of_col, self.col0_dev,
+                                    self.uvals64, self.bg.to(torch.float64).contiguous())
+
     def csr_physical32(self):
         if self._csr is None:
             ip, ix, v = self.csr()
@@ -343,6 +388,7 @@ class SparseU:
                 z[: self.n_local, :n].zero_()
             ops.project_local(movie2d, self.d2, self.starts_dev, self.bh, self.bw, self.ranks_dev, self.col0_dev, self.tasks,
                               self.uvals32, mean, inv_std, z[: self.n_local])
+            _submark("project.local")
         zb = z[self.n_local :]
         zb[:, :n].zero_()
         ops.project_dense(movie2d, self.bg, mean, inv_std, zb)
@@ -357,24 +403,19 @@ def compute_lowrank_factorized_svd(u, v, only_left=False):
     dev = u.uvals32.device
     v = _as_dev(v, dev)
     R = u.n_cols
-    right = v if R > v.shape[1] else torch.eye(R, dtype=torch.float32, device=dev)
-    m = right.shape[1]
-    wmov = u.apply(right)  # (m, d): columns of U right as frames
-    z = torch.empty((R, m), dtype=torch.float32, device=dev)
-    u.project(wmov, None, None, z)  # U^T U right
-    del wmov
+    right = v.to(torch.float64) if R > v.shape[1] else torch.eye(R, dtype=torch.float64, device=dev)
+    z = u.utu_times_f64(right)  # (R, m) float64
     g = torch.matmul(right.t(), z)
     g = 0.5 * (g + g.t())
     vals, vecs = sym_eigh_desc_abs(g)
-    good = vals > 0
+    # "eig_vals > 0" (decomposition.py:988) evaluated in float64: drop what is numerically zero
+    good = vals > vals[0] * 1e-13
     vals, vecs = vals[good], vecs[:, good]
-    mix = torch.matmul(right, vecs) / torch.sqrt(vals)[None, :]
+    mix64 = torch.matmul(right, vecs) / torch.sqrt(vals)[None, :]
+    mix = mix64.to(torch.float32)
     if only_left:
         return mix
-    wmov = u.apply(v)
-    zz = torch.empty((R, v.shape[1]), dtype=torch.float32, device=dev)
-    u.project(wmov, None, None, zz)
-    new_temporal = torch.matmul(mix.t(), zz)
+    new_temporal = torch.matmul(mix64.t(), u.utu_times_f64(v.to(torch.float64))).to(torch.float32)
     return projected_svd(mix, new_temporal)
 
 
@@ -407,21 +448,26 @@ def projected_svd(projection, data, group=None):
         dist.all_reduce(nt, group=group)
         n_total = int(nt.item())
     if k <= n_total:
-        gram = torch.matmul(data, data.t())
+        d64 = data.to(torch.float64)
+        gram = torch.matmul(d64, d64.t())
+        del d64
         if group is not None:
             dist.all_reduce(gram, group=group)
         gram = 0.5 * (gram + gram.t())
         vals, left = sym_eigh_desc_abs(gram)
-        sing = torch.sqrt(vals)
+        sing = torch.sqrt(vals).to(torch.float32)
+        left = left.to(torch.float32)
         div = torch.where(sing == 0, torch.ones_like(sing), sing)
         right = torch.matmul(left.t(), data) / div[:, None]
         return torch.matmul(projection, left), sing, right
     if group is not None:
         raise NotImplementedError("frame-sharded projected_svd needs k <= T")
-    gram = torch.matmul(data.t(), data)
+    d64 = data.to(torch.float64)
+    gram = torch.matmul(d64.t(), d64)
     gram = 0.5 * (gram + gram.t())
     vals, right_t = sym_eigh_desc_abs(gram)
-    sing = torch.sqrt(vals)
+    sing = torch.sqrt(vals).to(torch.float32)
+    right_t = right_t.to(torch.float32)
     div = torch.where(sing == 0, torch.ones_like(sing), sing)
     left = torch.matmul(data, right_t / div[None, :])
     return torch.matmul(projection, left), sing, right_t.t().contiguous()
@@ -490,7 +536,9 @@ def localmd_decomposition(
     take = lambda name: getattr(draws, name, None)  # noqa: E731
 
     with torch.cuda.device(dev):
+        global _ACTIVE_TIMER
         tm = _Timer(timings, dev)
+        _ACTIVE_TIMER = tm
         tm.mark("start")
         movie = dataset_obj if isinstance(dataset_obj, DeviceMovie) else DeviceMovie(dataset_obj, dev, batch_frames=max(1024, frame_batch_size))
         tm.mark("upload")
@@ -599,6 +647,9 @@ def localmd_decomposition(
         v_init = torch.cat([v_blk[blk_of_col, comp_of_col], vbg[:, :crop]], dim=0)  # (R, t)
         del u_blk, v_blk, yres
         say("The total rank before pruning is {}".format(su.n_cols))
+        if timings is not None:
+            timings["__info__"] = dict(n_cols=int(su.n_cols), n_local=int(su.n_local), nb=int(nb), mean_rank=float(ranks_host.mean()),
+                                       max_rank=int(ranks_host.max()))
         tm.mark("assemble")
 
         # ---- orthogonalisation (decomposition.py:860-881) -------------------------------------------
@@ -633,14 +684,12 @@ def localmd_decomposition(
         # ---- result object ---------------------------------------------------------------------------
         row_ids = torch.from_numpy(np.arange(d).reshape((d1, d2), order=order).reshape(-1)).to(dev)
         indptr, indices, values = su.csr(row_ids)
-        u_host = scipy.sparse.csr_matrix(
-            (values.cpu().numpy(), indices.cpu().numpy(), indptr.cpu().numpy().astype(np.int32)), shape=(d, su.n_cols)
-        )
-        mean_img = mean.cpu().numpy().reshape(d1, d2)
-        std_img = std.cpu().numpy().reshape(d1, d2)
-        out = PMDArray(u_host, rmix.cpu().numpy(), s.cpu().numpy(), vt.cpu().numpy(), (T, d1, d2), order, mean_img, std_img, device=dev)
+        _submark("export.csr")
+        out = PMDArray._from_device((indptr, indices, values), su.csr_physical32(), rmix.contiguous(), s.contiguous(),
+                                    vt.contiguous(), (T, d1, d2), order, mean, std, dev)
         tm.mark("export")
         tm.finish()
+        _ACTIVE_TIMER = None
         if details is not None:
             details.update(
                 ranks=ranks_host.astype(np.int32), block_starts=[tuple(x) for x in starts.tolist()], thresholds=(thr_s, thr_t),
@@ -672,6 +721,8 @@ def project_movie(movie: DeviceMovie, su: SparseU, p, mean, inv_std):
         n = chunk.shape[0]
         z = torch.empty((su.n_cols, n), dtype=torch.float32, device=dev)
         su.project(chunk, mean, inv_std, z)
+        _submark("projection.spmm")
         v_full[:, f0 : f0 + n].copy_(torch.matmul(pt, z))
+        _submark("projection.mix")
         del z
     return v_full

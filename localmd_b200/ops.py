@@ -268,3 +268,26 @@ def reconstruct(indptr, indices, values, c, pix, scale, shift):
     _call("pmd_reconstruct", _p(indptr), _p(indices), _p(values), _p(c), n, _p(pix), npix, _p(scale), _p(shift), _p(out),
           _stream())
     return out
+
+
+def reconstruct_f64(indptr, indices, values64, c64, pix):
+    """(n, npix) float64 = (U[pix] @ c)^T with float64 CSR values and coefficients (whitening step)."""
+    _req(indptr, torch.int64, "indptr"), _req(indices, torch.int32, "indices"), _req(values64, torch.float64, "values")
+    _req(c64, torch.float64, "c"), _req(pix, torch.int32, "pix")
+    n = c64.shape[1]
+    out = torch.empty((n, pix.numel()), dtype=torch.float64, device=c64.device)
+    _call("pmd_reconstruct_f64", _p(indptr), _p(indices), _p(values64), _p(c64), n, _p(pix), pix.numel(), _p(out), _stream())
+    return out
+
+
+def project_cols_f64(w64, d2, starts, bh, bw, blk_of_col, col0, uvals64, bg64):
+    """Z (n_cols, m) float64 = U^T w64^T for w64 (m, d) float64."""
+    _req(w64, torch.float64, "w"), _req(uvals64, torch.float64, "uvals64"), _req(bg64, torch.float64, "bg64")
+    _req(blk_of_col, torch.int32, "blk_of_col")
+    m, d = w64.shape
+    n_local = uvals64.shape[0]
+    n_cols = n_local + bg64.shape[0]
+    z = torch.empty((n_cols, m), dtype=torch.float64, device=w64.device)
+    _call("pmd_project_cols_f64", _p(w64), m, d2, d, _p(starts), bh, bw, _p(blk_of_col), _p(col0), n_local, _p(uvals64),
+          _p(bg64), n_cols, _p(z), _stream())
+    return z

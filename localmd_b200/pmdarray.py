@@ -33,22 +33,73 @@ class PMDArray:
         self._phys_indices = np.arange(d).reshape((self.fov_dim1, self.fov_dim2))
         self._device = device
         self._dev = None
+        self._lazy = None
+
+    @classmethod
+    def _from_device(cls, csr_order, csr_phys32, rmix, s, vt, data_shape, data_order, mean, std, device):
+        """Build from device-resident factors without any device->host copy: the host views (u, r, s, v)
+        are materialised on first access through pinned buffers.  csr_order = (indptr, indices, values64)
+        with rows numbered in `data_order`; csr_phys32 = the same matrix over physical pixel rows, float32."""
+        self = cls.__new__(cls)
+        self.order = data_order
+        self.num_frames, self.fov_dim1, self.fov_dim2 = (int(x) for x in data_shape)
+        d = self.fov_dim1 * self.fov_dim2
+        self._u = self._r = self._s = self._v = None
+        self._lazy = dict(csr=csr_order, r=rmix, s=s, v=vt, n_cols=int(rmix.shape[0]))
+        self.mean_img = mean.cpu().numpy().reshape(self.fov_dim1, self.fov_dim2)
+        self.var_img = std.cpu().numpy().reshape(self.fov_dim1, self.fov_dim2)
+        self.row_indices = np.arange(d).reshape((self.fov_dim1, self.fov_dim2), order=self.order)
+        self._phys_indices = np.arange(d).reshape((self.fov_dim1, self.fov_dim2))
+        self._device = device
+        ip, ix, v32 = csr_phys32
+        self._dev = dict(device=torch.device(device), indptr=ip, indices=ix, values=v32,
+                         rs=(rmix * s[None, :]).contiguous(), vt=vt.contiguous(), mean=mean.contiguous(), std=std.contiguous())
+        return self
+
+    @staticmethod
+    def _to_host(t):
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        buf.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return buf.numpy()
+
+    def _materialise(self, what):
+        lz = self._lazy
+        if what == "u" and self._u is None:
+            ip, ix, v = lz["csr"]
+            d = self.fov_dim1 * self.fov_dim2
+            self._u = scipy.sparse.csr_matrix(
+                (self._to_host(v), self._to_host(ix), self._to_host(ip).astype(np.int32)), shape=(d, lz["n_cols"]))
+        elif what == "r" and self._r is None:
+            self._r = self._to_host(lz["r"])
+        elif what == "s" and self._s is None:
+            self._s = self._to_host(lz["s"])
+        elif what == "v" and self._v is None:
+            self._v = self._to_host(lz["v"])
 
     # ---- reference properties -------------------------------------------------------------------
     @property
     def u(self):
+        if self._u is None:
+            self._materialise("u")
         return self._u
 
     @property
     def r(self):
+        if self._r is None:
+            self._materialise("r")
         return self._r
 
     @property
     def s(self):
+        if self._s is None:
+            self._materialise("s")
         return self._s
 
     @property
     def v(self):
+        if self._v is None:
+            self._materialise("v")
         return self._v
 
     @property
@@ -71,15 +122,15 @@ class PMDArray:
             dev = torch.device(self._device if self._device is not None else "cuda")
             # CSR rows are numbered in `order`; the kernels index physical (row-major) pixels
             perm = self.row_indices.reshape(-1)  # physical pixel p -> row id in `order`
-            u_phys = self._u[perm].tocsr()
+            u_phys = self.u[perm].tocsr()
             u_phys.sort_indices()
             self._dev = dict(
                 device=dev,
                 indptr=torch.from_numpy(u_phys.indptr.astype(np.int64)).to(dev),
                 indices=torch.from_numpy(u_phys.indices.astype(np.int32)).to(dev),
                 values=torch.from_numpy(u_phys.data.astype(np.float32)).to(dev),
-                rs=torch.from_numpy(np.ascontiguousarray(self._r * self._s[None, :], dtype=np.float32)).to(dev),
-                vt=torch.from_numpy(np.ascontiguousarray(self._v, dtype=np.float32)).to(dev),
+                rs=torch.from_numpy(np.ascontiguousarray(self.r * self.s[None, :], dtype=np.float32)).to(dev),
+                vt=torch.from_numpy(np.ascontiguousarray(self.v, dtype=np.float32)).to(dev),
                 mean=torch.from_numpy(np.ascontiguousarray(self.mean_img, dtype=np.float32).reshape(-1)).to(dev),
                 std=torch.from_numpy(np.ascontiguousarray(self.var_img, dtype=np.float32).reshape(-1)).to(dev),
             )

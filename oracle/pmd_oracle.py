@@ -21,6 +21,7 @@ Randomness is never drawn here implicitly: every random quantity is an explicit 
 """
 from __future__ import annotations
 
+import contextlib
 import math
 from dataclasses import dataclass, field
 from typing import Callable, List, Optional, Sequence, Tuple
@@ -29,7 +30,22 @@ import numpy as np
 import scipy.signal
 import scipy.sparse as sp
 
-F32 = np.float32
+F32 = np.float32  # working precision of the restatement; see precision()
+
+
+@contextlib.contextmanager
+def precision(dtype):
+    """Run the restated algorithm in another working precision.  precision(np.float64) evaluates the
+    reference's algorithm (same control flow, same draws) in double: the tests use it as the
+    exact-arithmetic answer, to separate 'differs from the reference algorithm' from 'differs by the
+    reference's own float32 rounding'."""
+    global F32
+    old = F32
+    F32 = np.dtype(dtype).type
+    try:
+        yield
+    finally:
+        F32 = old
 
 
 # --------------------------------------------------------------------------------------------

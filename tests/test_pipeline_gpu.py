@@ -36,8 +36,19 @@ def run_case(name):
                                                  timings=timings, **kw)
         okw = {k: v for k, v in kw.items() if k != "pixel_batch_size"}
         ref = O.localmd_decomposition_oracle(movie, spec["block_sizes"], spec["frame_range"], d, **okw)
-        _cache[name] = (g, spec, movie, arr, details, ref)
+        with O.precision(np.float64):  # the reference algorithm in exact(ish) arithmetic, same draws
+            ref64 = O.localmd_decomposition_oracle(movie, spec["block_sizes"], spec["frame_range"], d, **okw)
+        _cache[name] = (g, spec, movie, arr, details, ref, ref64)
     return _cache[name]
+
+
+def run5(name):
+    return run_case(name)[:6]
+
+
+def recon_norm(u, r, s, vt):
+    """Reconstruction in normalised units (mean removed, noise-std units), full movie, float64."""
+    return (u @ (np.asarray(r) * np.asarray(s)[None]).astype(np.float64)) @ np.asarray(vt).astype(np.float64)
 
 
 def principal_angles(a, b):
@@ -54,7 +65,7 @@ def near_threshold_blocks(details, thr):
 
 @pytest.mark.parametrize("name", GPU_CASES)
 def test_stats_background_thresholds(name):
-    g, spec, movie, arr, det, ref = run_case(name)
+    g, spec, movie, arr, det, ref = run5(name)
     np.testing.assert_allclose(arr.mean_img, ref.mean_img, rtol=2e-6)
     np.testing.assert_allclose(arr.var_img, ref.std_img, rtol=2e-5)
     np.testing.assert_allclose(arr.mean_img, g["mean_img"], rtol=2e-6)
@@ -68,7 +79,7 @@ def test_stats_background_thresholds(name):
 
 @pytest.mark.parametrize("name", GPU_CASES)
 def test_ranks_and_structure(name):
-    g, spec, movie, arr, det, ref = run_case(name)
+    g, spec, movie, arr, det, ref = run5(name)
     near = near_threshold_blocks(det, ref.thresholds)
     same = det["ranks"] == ref.ranks
     assert np.all(same | near), (det["ranks"].tolist(), ref.ranks.tolist())
@@ -88,7 +99,7 @@ def test_ranks_and_structure(name):
 def test_local_subspaces_match(name):
     """Per block, the kept spatial components span the same subspace as the oracle's (the leading,
     well separated components to 1e-3 rad)."""
-    g, spec, movie, arr, det, ref = run_case(name)
+    g, spec, movie, arr, det, ref = run5(name)
     if not np.array_equal(det["ranks"], ref.ranks):
         pytest.skip("rank differs inside the threshold band")
     ud, ur = arr.u.toarray(), ref.u.toarray()
@@ -104,33 +115,49 @@ def test_local_subspaces_match(name):
 
 @pytest.mark.parametrize("name", GPU_CASES)
 def test_singular_values_subspaces_reconstruction(name):
-    g, spec, movie, arr, det, ref = run_case(name)
-    if not np.array_equal(det["ranks"], ref.ranks):
+    """north_star tolerances.  Every quantity is compared (a) with the reference algorithm evaluated in
+    float64 on the same draws -- tolerance as stated -- and (b) with its float32 evaluation (oracle and
+    reference-run fixture), where the allowance is widened by the float32 evaluation's own measured
+    distance from (a): the reference's LAPACK-float32 SVDs of kappa ~ 1e3 matrices are themselves only
+    good to a few 1e-4 ('numerics')."""
+    g, spec, movie, arr, det, ref, ref64 = run_case(name)
+    if not np.array_equal(det["ranks"], ref64.ranks):
         pytest.skip("rank differs inside the threshold band")
-    k = min(len(arr.s), len(ref.s))
-    assert abs(len(arr.s) - len(ref.s)) <= max(2, len(ref.s) // 50)
-    lead = ref.s[:k] > 0.05 * ref.s[0]  # Gram-based float32 SVD: relative accuracy eps * (s0/si)^2
-    np.testing.assert_allclose(arr.s[:k][lead], ref.s[:k][lead], rtol=1e-4)
-    nl = int(lead.sum())
-    ur_d = arr.u @ arr.r[:, :nl].astype(np.float64)
-    ur_o = ref.u @ ref.r[:, :nl].astype(np.float64)
-    well = name != "wide_R"  # R > t: the float32 whitening of the reference itself is ill conditioned
+    well = name != "wide_R"  # R > t: Gram whitening of a numerically rank-deficient matrix (ill posed)
+    assert abs(len(arr.s) - len(ref64.s)) <= max(2, len(ref64.s) // 50)
+    k = min(len(arr.s), len(ref64.s), len(ref.s))
+    lead = ref64.s[:k] > 0.05 * ref64.s[0]
+    tol_s = 1e-4 if well else 2e-3
+    np.testing.assert_allclose(arr.s[:k][lead], ref64.s[:k][lead], rtol=tol_s)
+    slack32 = np.abs(ref.s[:k][lead] / ref64.s[:k][lead] - 1).max()
+    np.testing.assert_allclose(arr.s[:k][lead], ref.s[:k][lead], rtol=tol_s + 2 * slack32)
+    y64 = recon_norm(ref64.u, ref64.r, ref64.s, ref64.vt)
+    y32 = recon_norm(ref.u, ref.r, ref.s, ref.vt)
+    yd = recon_norm(arr.u, arr.r, arr.s, arr.v)
+    n = np.linalg.norm(y64)
+    err64, err32, slack = np.linalg.norm(yd - y64) / n, np.linalg.norm(yd - y32) / n, np.linalg.norm(y32 - y64) / n
+    print("%s: recon err vs f64 oracle %.2e, vs f32 oracle %.2e (f32 oracle vs f64 oracle %.2e)" % (name, err64, err32, slack))
     if well:
+        assert err64 < 1e-4, err64
+        assert err32 < 1e-4 + 1.5 * slack, (err32, slack)
+        yg = recon_norm(sp.csr_matrix((g["U_data"], g["U_indices"], g["U_indptr"]), shape=tuple(g["U_shape"])), g["R"], g["s"], g["Vt"])
+        assert np.linalg.norm(yd - yg) / n < 1e-4 + 1.5 * slack
+        # principal angles of the leading singular subspaces, cut at the widest spectral gap of the lead set
+        gaps = ref64.s[: lead.sum() - 1] / ref64.s[1 : lead.sum()]
+        nl = int(np.argmax(gaps)) + 1
+        ur_d = arr.u @ arr.r[:, :nl].astype(np.float64)
+        ur_o = ref64.u @ ref64.r[:, :nl].astype(np.float64)
         assert principal_angles(ur_d, ur_o).max() < 1e-3
-        assert principal_angles(arr.v[:nl].T.astype(np.float64), ref.vt[:nl].T.astype(np.float64)).max() < 1e-3
-    # reconstruction in normalised units (mean removed, noise-std units), full movie
-    yd = (arr.u @ (arr.r * arr.s[None]).astype(np.float64)) @ arr.v.astype(np.float64)
-    yo = (ref.u @ (ref.r * ref.s[None]).astype(np.float64)) @ ref.vt.astype(np.float64)
-    err = np.linalg.norm(yd - yo) / np.linalg.norm(yo)
-    assert err < (1e-4 if well else 5e-2), err
-    yg = (sp.csr_matrix((g["U_data"], g["U_indices"], g["U_indptr"]), shape=tuple(g["U_shape"])) @ (g["R"] * g["s"][None]).astype(np.float64)) @ g["Vt"].astype(np.float64)
-    errg = np.linalg.norm(yd - yg) / np.linalg.norm(yg)
-    assert errg < (1e-4 if well else 5e-2), errg
+        assert principal_angles(arr.v[:nl].T.astype(np.float64), ref64.vt[:nl].T.astype(np.float64)).max() < 1e-3
+    else:
+        # the float32 reference itself is off by `slack` (tens of percent) here; the float64 whitening keeps
+        # us at the stated tolerance against the exact-arithmetic answer
+        assert err64 < 1e-4 and err64 < 0.01 * slack, (err64, slack)
 
 
 @pytest.mark.parametrize("name", GPU_CASES)
 def test_output_invariants(name):
-    g, spec, movie, arr, det, ref = run_case(name)
+    g, spec, movie, arr, det, ref = run5(name)
     s = arr.s
     assert np.all(np.diff(s) <= 0) and np.all(s > 0)
     assert arr.r.dtype == np.float32 and arr.s.dtype == np.float32 and arr.v.dtype == np.float32
@@ -156,7 +183,7 @@ def test_output_invariants(name):
 def test_pmdarray_slicing_and_npz(name):
     import localmd_b200
 
-    g, spec, movie, arr, det, ref = run_case(name)
+    g, spec, movie, arr, det, ref = run5(name)
     po = O.PMDArrayOracle(arr.u, arr.r, arr.s, arr.v, arr.shape, arr.order, arr.mean_img, arr.var_img)
     keys = [
         (slice(None), 5, 7), (3, slice(None), slice(None)), (slice(10, 20), slice(3, 9), slice(4, 15)), ([1, 5, 9],),

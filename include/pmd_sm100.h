@@ -131,6 +131,17 @@ int pmd_project_local(const void* movie, int dtype, int64_t t, int64_t d2, int64
                       const int32_t* tasks, int64_t n_tasks, const float* uvals32, const float* mean,
                       const float* inv_std, float* z, int64_t ldz, void* stream);
 
+/* K7a (v2)  same contraction as pmd_project_local, organised by SUPERTILES of neighbouring blocks whose
+ * pixel union is staged once per frame sub-tile in shared memory (centred and scaled there).
+ * tiles: [n_tiles][4] int32 = (r0, c0, rh, rw) pixel region of each supertile (rh*rw <= 2048);
+ * task_ptr: [n_tiles+1] int32 offsets into tasks; tasks: [n_tasks][4] int32 = (row offset of the block inside
+ * the region, column offset, first output column, number of components 1..4).  Built by the host
+ * (localmd_b200/ops.py: make_supertiles).  bh*bw <= 512.  Every z element of a listed column is written once. */
+int pmd_project_supertile(const void* movie, int dtype, int64_t t, int64_t d2, int64_t d, const int32_t* tiles,
+                          int64_t n_tiles, const int32_t* task_ptr, const int32_t* tasks, int64_t bh, int64_t bw,
+                          int64_t max_region_h, int64_t max_region_w, const float* uvals32, const float* mean,
+                          const float* inv_std, float* z, int64_t ldz, void* stream);
+
 /* K7b  full-movie projection onto dense (background) columns:
  *   z[c][f] += sum_p basis[c][p] * (movie[f][p] - mean[p]) * inv_std[p]     (c < k <= 16)
  * replaces: the same v_projection for the dense background columns appended at

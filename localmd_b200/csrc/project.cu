@@ -126,25 +126,29 @@ project_dense_kernel(const T* __restrict__ movie, int64_t t, int64_t d, const fl
     const int64_t f_end = min(f_begin + kDenseFrames, t);
     for (int64_t fb = f_begin; fb < f_end; fb += 2 * kDenseBatch) {
 #pragma unroll
-        for (int st = 0; st < kDenseBatch; ++st) {
-            float acc[32];
+        for (int sp = 0; sp < kDenseBatch / 2; ++sp) {
+            // issue the loads of 4 frames up front (memory-level parallelism), then two 2-frame reductions
+            float xs[4][4];
 #pragma unroll
-            for (int q = 0; q < 32; ++q) acc[q] = 0.f;
+            for (int g = 0; g < 4; ++g) {
+                const int64_t f = fb + 4 * sp + g;
+                const T* fr = movie + f * d + p0;
 #pragma unroll
-            for (int g = 0; g < 2; ++g) {
-                const int64_t f = fb + 2 * st + g;
-                if (f < f_end) {
-                    const T* fr = movie + f * d + p0;
-                    float x[4];
+                for (int j = 0; j < 4; ++j) xs[g][j] = (ok[j] && f < f_end) ? to_f32(fr[j]) - mu[j] : 0.f;
+            }
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) x[j] = ok[j] ? to_f32(fr[j]) - mu[j] : 0.f;
+            for (int h = 0; h < 2; ++h) {
+                float acc[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) acc[q] = 0.f;
+#pragma unroll
+                for (int g = 0; g < 2; ++g)
 #pragma unroll
                     for (int c = 0; c < 16; ++c)
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[g * 16 + c] = fmaf(bs[c][j], x[j], acc[g * 16 + c]);
-                }
+                        for (int j = 0; j < 4; ++j) acc[g * 16 + c] = fmaf(bs[c][j], xs[2 * h + g][j], acc[g * 16 + c]);
+                red[warp][2 * sp + h][lane] = transpose_reduce32(acc, lane);
             }
-            red[warp][st][lane] = transpose_reduce32(acc, lane);
         }
         __syncthreads();
         {
@@ -220,5 +224,175 @@ extern "C" int pmd_project_dense(const void* movie, int dtype, int64_t t, int64_
         pmd::project_dense_kernel<scalar_t><<<grid, pmd::kDenseWarps * 32, 0, st>>>((const scalar_t*)movie, t, d, basis, (int)k,
                                                                                     mean, inv_std, z, ldz);
     });
+    return pmd::check_launch(fn);
+}
+
+// =================================================================================================
+// K7 v2: supertile projection.
+//
+// v1 (project_local_kernel above) lets every (block, component group) warp fetch its own 20x20 window
+// from global memory, so every movie element crosses L2 -> SM about 4 x 1.6 times.  Here a CTA owns a
+// "supertile" of G x G neighbouring blocks and walks a frame range: per sub-tile of `ft` frames the
+// union of the blocks' windows (e.g. 40 x 40 pixels for G = 3, 20 x 20 blocks) is staged ONCE into
+// shared memory -- already centred and scaled, (y - mu) * (1/sigma) -- and then every warp applies the
+// U slice it keeps in registers (lane l owns block pixels l, l+32, ...) to all staged frames, 8 frames
+// per transpose-reduction.  Re-read factor from L2 drops from ~6.4 to (S / (S - overlap))^2 ~ 1.8, all
+// global loads are full row segments of the region, and the standardisation is done once per element.
+// Tasks = (block, group of <= 4 components); a warp normally owns exactly one task for the whole frame
+// range, so its U slice is loaded once per CTA.
+// =================================================================================================
+namespace pmd {
+
+constexpr int kSTWarps = 16;
+constexpr int kSTThreads = kSTWarps * 32;
+constexpr int kSTPixPerThread = 4;  // staged region <= 2048 pixels
+
+template <typename T, int PPL>
+__global__ void __launch_bounds__(kSTThreads, 1)
+project_supertile_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_t d, const int4* __restrict__ tiles,
+                         const int32_t* __restrict__ task_ptr, const int4* __restrict__ tasks, int bh, int bw,
+                         const float* __restrict__ uvals, const float* __restrict__ mean, const float* __restrict__ inv_std,
+                         float* __restrict__ z, int64_t ldz, int ft, int frames_per_cta, int rwp, int rp) {
+    extern __shared__ __align__(16) float stile[];  // [ft][rp]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int4 tl = tiles[blockIdx.x];
+    const int r0 = tl.x, c0 = tl.y, rh = tl.z, rw = tl.w;
+    const int npx = rh * rw;
+    const int bpix = bh * bw;
+
+    float smu[kSTPixPerThread], sis[kSTPixPerThread];
+    int goff[kSTPixPerThread], soff[kSTPixPerThread];
+    bool pv[kSTPixPerThread];
+#pragma unroll
+    for (int j = 0; j < kSTPixPerThread; ++j) {
+        const int p = tid + kSTThreads * j;
+        pv[j] = p < npx;
+        const int r = pv[j] ? p / rw : 0;
+        const int c = pv[j] ? p - r * rw : 0;
+        goff[j] = (r0 + r) * (int)d2 + c0 + c;
+        soff[j] = r * rwp + c;
+        smu[j] = (pv[j] && mean) ? mean[goff[j]] : 0.f;
+        sis[j] = (pv[j] && inv_std) ? inv_std[goff[j]] : 1.f;
+    }
+
+    const int tbeg = task_ptr[blockIdx.x], tend = task_ptr[blockIdx.x + 1];
+    int cached = -1, col = 0, nc = 0;
+    float uw[4][PPL];
+    int off[PPL];
+
+    const int64_t fbase = (int64_t)blockIdx.y * frames_per_cta;
+    const int64_t fend = min(t, fbase + frames_per_cta);
+    for (int64_t fs = fbase; fs < fend; fs += ft) {
+        const int nf = (int)min((int64_t)ft, fend - fs);
+        // ---- stage: centred + scaled region, one row segment per warp-load
+#pragma unroll 4
+        for (int f = 0; f < nf; ++f) {
+            const T* fr = movie + (fs + f) * d;
+#pragma unroll
+            for (int j = 0; j < kSTPixPerThread; ++j)
+                if (pv[j]) stile[f * rp + soff[j]] = (to_f32(fr[goff[j]]) - smu[j]) * sis[j];
+        }
+        __syncthreads();
+        // ---- compute
+        for (int ti = tbeg + warp; ti < tend; ti += kSTWarps) {
+            if (ti != cached) {
+                const int4 tk = tasks[ti];
+                col = tk.z;
+                nc = tk.w;
+#pragma unroll
+                for (int i = 0; i < PPL; ++i) {
+                    const int q = lane + 32 * i;
+                    const bool ok = q < bpix;
+                    const int qi = ok ? q / bw : 0;
+                    const int qj = ok ? q - qi * bw : 0;
+                    off[i] = (tk.x + qi) * rwp + tk.y + qj;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) uw[c][i] = (ok && c < nc) ? uvals[(int64_t)(col + c) * bpix + q] : 0.f;
+                }
+                cached = ti;
+            }
+            for (int fg = 0; fg < nf; fg += 8) {
+                float acc[32];
+#pragma unroll
+                for (int k = 0; k < 32; ++k) acc[k] = 0.f;
+                if (nc > 2) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        if (fg + g < nf) {
+                            const float* fr = stile + (fg + g) * rp;
+#pragma unroll
+                            for (int i = 0; i < PPL; ++i) {
+                                const float x = fr[off[i]];
+#pragma unroll
+                                for (int c = 0; c < 4; ++c) acc[g * 4 + c] = fmaf(uw[c][i], x, acc[g * 4 + c]);
+                            }
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        if (fg + g < nf) {
+                            const float* fr = stile + (fg + g) * rp;
+#pragma unroll
+                            for (int i = 0; i < PPL; ++i) {
+                                const float x = fr[off[i]];
+                                acc[g * 4 + 0] = fmaf(uw[0][i], x, acc[g * 4 + 0]);
+                                acc[g * 4 + 1] = fmaf(uw[1][i], x, acc[g * 4 + 1]);
+                            }
+                        }
+                    }
+                }
+                const float tot = transpose_reduce32(acc, lane);
+                const int g = lane >> 2, c = lane & 3;
+                if (c < nc && fg + g < nf) z[(int64_t)(col + c) * ldz + fs + fg + g] = tot;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace pmd
+
+extern "C" int pmd_project_supertile(const void* movie, int dtype, int64_t t, int64_t d2, int64_t d, const int32_t* tiles,
+                                     int64_t n_tiles, const int32_t* task_ptr, const int32_t* tasks, int64_t bh, int64_t bw,
+                                     int64_t max_region_h, int64_t max_region_w, const float* uvals32, const float* mean,
+                                     const float* inv_std, float* z, int64_t ldz, void* stream) {
+    const char* fn = "pmd_project_supertile";
+    PMD_REQUIRE(movie && tiles && task_ptr && tasks && uvals32 && z, fn, "null pointer");
+    PMD_REQUIRE(t > 0 && n_tiles > 0 && ldz >= t, fn, "bad size");
+    PMD_REQUIRE(d < (int64_t)1 << 31, fn, "frame too large for 32-bit pixel offsets");
+    PMD_REQUIRE(max_region_h * max_region_w <= pmd::kSTThreads * pmd::kSTPixPerThread, fn, "region larger than 2048 pixels");
+    const int64_t bpix = bh * bw;
+    PMD_REQUIRE(bpix <= 32 * 16, fn, "block larger than 512 pixels (use pmd_project_local)");
+    const int ppl = bpix <= 32 * 4 ? 4 : bpix <= 32 * 8 ? 8 : bpix <= 32 * 13 ? 13 : 16;
+    const int rwp = (int)max_region_w + 1;
+    const int rp = (int)max_region_h * rwp;
+    int ft = (int)((220 * 1024) / ((size_t)rp * sizeof(float)));
+    ft = std::min(64, ft / 8 * 8);
+    PMD_REQUIRE(ft >= 8, fn, "region does not fit shared memory");
+    const size_t smem = (size_t)ft * rp * sizeof(float);
+    const int frames_per_cta = std::max(ft, 512 / ft * ft);
+    const int64_t fsplits = (t + frames_per_cta - 1) / frames_per_cta;
+    PMD_REQUIRE(fsplits <= 65535, fn, "too many frames per call");
+    dim3 grid((unsigned)n_tiles, (unsigned)fsplits);
+    cudaStream_t st = (cudaStream_t)stream;
+#define PMD_LAUNCH_ST(PPL)                                                                                               \
+    {                                                                                                                    \
+        auto k = pmd::project_supertile_kernel<scalar_t, PPL>;                                                           \
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+        if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }         \
+        k<<<grid, pmd::kSTThreads, smem, st>>>((const scalar_t*)movie, t, d2, d, (const int4*)tiles, task_ptr,            \
+                                               (const int4*)tasks, (int)bh, (int)bw, uvals32, mean, inv_std, z, ldz, ft, \
+                                               frames_per_cta, rwp, rp);                                                 \
+    }
+    PMD_DISPATCH_DTYPE(dtype, fn, {
+        switch (ppl) {
+            case 4: PMD_LAUNCH_ST(4); break;
+            case 8: PMD_LAUNCH_ST(8); break;
+            case 13: PMD_LAUNCH_ST(13); break;
+            default: PMD_LAUNCH_ST(16); break;
+        }
+    });
+#undef PMD_LAUNCH_ST
     return pmd::check_launch(fn);
 }

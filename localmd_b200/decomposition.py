@@ -316,6 +316,15 @@ class SparseU:
         self.n_cols = self.n_local + bg.shape[0]
         self.tasks = torch.from_numpy(ops.make_tasks(ranks_host)).to(ranks_dev.device)
         self._csr = None
+        self.supertiles = None
+        if len(ranks_host) and bh * bw <= 512:
+            rows = sorted(set(int(x) for x in starts[:, 0]))
+            cols = sorted(set(int(x) for x in starts[:, 1]))
+            if len(rows) * len(cols) == len(ranks_host):
+                st = ops.make_supertiles(rows, cols, bh, bw, ranks_host, self.col0_host)
+                if st["max_h"] * st["max_w"] <= 2048:
+                    self.supertiles = {k: (torch.from_numpy(v).to(ranks_dev.device) if isinstance(v, np.ndarray) else v)
+                                       for k, v in st.items()}
 
     def coo_physical(self):
         """(rows = physical pixel ids, cols, float64 values) of all stored entries, exact zeros dropped
@@ -384,10 +393,14 @@ class SparseU:
         """z[:, :n] (R, ldz) (+)= U^T standardised(movie2d)   (K7a + K7b)."""
         n = movie2d.shape[0]
         if self.n_local > 0:
-            if self.bh * self.bw > 512:
-                z[: self.n_local, :n].zero_()
-            ops.project_local(movie2d, self.d2, self.starts_dev, self.bh, self.bw, self.ranks_dev, self.col0_dev, self.tasks,
-                              self.uvals32, mean, inv_std, z[: self.n_local])
+            if self.supertiles is not None:
+                ops.project_supertile(movie2d, self.d2, self.supertiles, self.bh, self.bw, self.uvals32, mean, inv_std,
+                                      z[: self.n_local])
+            else:
+                if self.bh * self.bw > 512:
+                    z[: self.n_local, :n].zero_()
+                ops.project_local(movie2d, self.d2, self.starts_dev, self.bh, self.bw, self.ranks_dev, self.col0_dev,
+                                  self.tasks, self.uvals32, mean, inv_std, z[: self.n_local])
             _submark("project.local")
         zb = z[self.n_local :]
         zb[:, :n].zero_()

@@ -291,3 +291,60 @@ def project_cols_f64(w64, d2, starts, bh, bw, blk_of_col, col0, uvals64, bg64):
     _call("pmd_project_cols_f64", _p(w64), m, d2, d, _p(starts), bh, bw, _p(blk_of_col), _p(col0), n_local, _p(uvals64),
           _p(bg64), n_cols, _p(z), _stream())
     return z
+
+
+def split_groups(rk):
+    """Split `rk` kept components into ceil(rk/4) groups of nearly equal size (each <= 4)."""
+    ng = (rk + 3) // 4
+    base, extra = divmod(rk, ng)
+    return [base + (1 if i < extra else 0) for i in range(ng)]
+
+
+def make_supertiles(row_starts, col_starts, bh, bw, ranks_host, col0_host, max_pixels=2048, target_tasks=14):
+    """Host tables for pmd_project_supertile: group G x G neighbouring blocks (block grid = row_starts x col_starts,
+    blocks numbered row-major) so that the staged pixel region stays <= max_pixels and the mean number of
+    (block, component group) tasks per supertile is about `target_tasks` (one task per warp).
+    Returns dict(tiles int32 [n,4], task_ptr int32 [n+1], tasks int32 [m,4], max_h, max_w, G)."""
+    row_starts, col_starts = list(row_starts), list(col_starts)
+    nbr, nbc = len(row_starts), len(col_starts)
+    ranks_host = np.asarray(ranks_host, dtype=np.int64).reshape(nbr, nbc)
+    col0_host = np.asarray(col0_host, dtype=np.int64).reshape(nbr, nbc)
+    groups_per_block = float(np.mean((ranks_host + 3) // 4))
+
+    def region(g):
+        h = max(row_starts[min(a + g, nbr) - 1] + bh - row_starts[a] for a in range(0, nbr, g))
+        w = max(col_starts[min(c + g, nbc) - 1] + bw - col_starts[c] for c in range(0, nbc, g))
+        return h, w
+
+    G = 1
+    for g in range(2, 9):
+        h, w = region(g)
+        if h * w > max_pixels or g * g * groups_per_block > target_tasks * 1.15:
+            break
+        G = g
+    tiles, task_ptr, tasks = [], [0], []
+    for a0 in range(0, nbr, G):
+        for c0 in range(0, nbc, G):
+            a1, c1 = min(a0 + G, nbr), min(c0 + G, nbc)
+            r0, cc0 = row_starts[a0], col_starts[c0]
+            tiles.append((r0, cc0, row_starts[a1 - 1] + bh - r0, col_starts[c1 - 1] + bw - cc0))
+            for a in range(a0, a1):
+                for c in range(c0, c1):
+                    first = int(col0_host[a, c])
+                    for n in split_groups(int(ranks_host[a, c])):
+                        tasks.append((row_starts[a] - r0, col_starts[c] - cc0, first, n))
+                        first += n
+            task_ptr.append(len(tasks))
+    tiles = np.array(tiles, dtype=np.int32).reshape(-1, 4)
+    return dict(tiles=tiles, task_ptr=np.array(task_ptr, dtype=np.int32), tasks=np.array(tasks, dtype=np.int32).reshape(-1, 4),
+                max_h=int(tiles[:, 2].max()), max_w=int(tiles[:, 3].max()), G=G)
+
+
+def project_supertile(movie2d, d2, st, bh, bw, uvals32, mean, inv_std, z):
+    """z[col, f] = U_loc^T standardised movie via the supertile kernel; `st` = device copies of make_supertiles()."""
+    t, d = movie2d.shape
+    _req(uvals32, torch.float32, "uvals32")
+    assert z.dtype == torch.float32 and z.stride(1) == 1
+    _call("pmd_project_supertile", _p(movie2d), movie_dtype_code(movie2d), t, d2, d, _p(st["tiles"]), st["tiles"].shape[0],
+          _p(st["task_ptr"]), _p(st["tasks"]), bh, bw, st["max_h"], st["max_w"], _p(uvals32), _p(mean), _p(inv_std), _p(z),
+          z.stride(0), _stream())

@@ -1,0 +1,161 @@
+"""CPU tests of the host-side logic and of the C-ABI library itself (no compute calls without a GPU):
+the shared library loads and exports every symbol include/pmd_sm100.h declares, the host tables
+(tiling, weights, task lists, supertiles, Welch tables) agree with the oracle, the .npz layout and the
+PMDArray container work, and compute entry points fail loudly without a CUDA device."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+
+import oracle.pmd_oracle as O
+
+
+def test_library_exports_every_declared_symbol():
+    import __graft_entry__
+
+    __graft_entry__.build()
+    from localmd_b200 import _lib
+
+    names = _lib.declared_symbols()
+    assert len(names) >= 17 and "pmd_project_supertile" in names and "pmd_stats_pass" in names
+    L = _lib.lib()
+    for n in names:
+        assert hasattr(L, n), n
+    assert L.pmd_abi_version() == 1
+    sigs = _lib._parse_header()
+    assert sigs["pmd_reconstruct"] == "pppplplpppp"
+
+
+def test_null_pointer_is_rejected_without_touching_the_gpu():
+    from localmd_b200 import _lib
+
+    L = _lib.lib()
+    rc = L.pmd_stats_pass(None, 0, 10, 10, 10, None, None, None, None, None)
+    assert rc < 0 and b"null pointer" in L.pmd_last_error()
+    rc = L.pmd_gram_f64(None, 1, 500, 10, 1, 1, 1, None, None)
+    assert rc < 0
+
+
+def test_host_geometry_matches_oracle():
+    from localmd_b200 import decomposition as D
+
+    for n, b in [(512, 20), (512, 32), (1024, 40), (150, 32), (150, 28), (150, 40), (24, 24), (60, 20), (80, 20)]:
+        assert D.tile_starts(n, b) == O.tile_starts(n, b)
+    for bh, bw in [(20, 20), (12, 20), (32, 32), (10, 14)]:
+        np.testing.assert_array_equal(D.pyramid_weights(bh, bw), O.pyramid_weights(bh, bw))
+    with pytest.raises(ValueError):
+        D.pyramid_weights(21, 20)
+    with pytest.raises(ValueError):
+        D.check_fov_size((9, 20))
+    with pytest.raises(ValueError):
+        D.update_block_sizes([9, 20], (100, 100))
+    assert D.update_block_sizes([32, 32], (24, 20)) == [24, 20]
+    rng = np.random.default_rng(0)
+    fr = D.identify_window_chunks(600, 1300, 600, rng)
+    assert len(fr) == 600 and fr[0] in (0, 600, 700) and fr == list(range(fr[0], fr[0] + 600))
+    assert D.identify_window_chunks(400, 1300, 200, rng, starting_points=[800, 200]) == list(range(200, 400)) + list(range(800, 1000))
+    with pytest.raises(ValueError):
+        D.identify_window_chunks(2000, 1300, 2000, rng)
+
+
+def test_task_tables():
+    from localmd_b200 import ops
+
+    assert ops.make_tasks([3, 5, 1, 8]).tolist() == [[0, 0], [1, 0], [1, 4], [2, 0], [3, 0], [3, 4]]
+    assert [ops.split_groups(k) for k in (1, 4, 5, 6, 7, 9, 13)] == [[1], [4], [3, 2], [3, 3], [4, 3], [3, 3, 3], [4, 3, 3, 3]]
+    rng = np.random.default_rng(1)
+    for d1, d2, bh, bw in [(512, 512, 20, 20), (61, 83, 16, 16), (150, 150, 32, 28), (20, 20, 20, 20), (64, 40, 20, 12)]:
+        rows, cols = O.tile_starts(d1, bh), O.tile_starts(d2, bw)
+        nb = len(rows) * len(cols)
+        ranks = rng.integers(1, 14, nb)
+        col0 = np.concatenate([[0], np.cumsum(ranks)[:-1]])
+        st = ops.make_supertiles(rows, cols, bh, bw, ranks, col0)
+        assert st["max_h"] * st["max_w"] <= 2048 or st["G"] == 1
+        covered = np.zeros(int(ranks.sum()), dtype=int)
+        for ti, (r0, c0, rh, rw) in enumerate(st["tiles"]):
+            assert r0 + rh <= d1 and c0 + rw <= d2
+            for qi0, qj0, col, nc in st["tasks"][st["task_ptr"][ti] : st["task_ptr"][ti + 1]]:
+                assert 0 <= qi0 and qi0 + bh <= rh and 0 <= qj0 and qj0 + bw <= rw and 1 <= nc <= 4
+                b = np.searchsorted(col0, col, side="right") - 1
+                assert (r0 + qi0, c0 + qj0) == (rows[b // len(cols)], cols[b % len(cols)])
+                covered[col : col + nc] += 1
+        assert np.all(covered == 1)  # every kept component is projected exactly once
+
+
+def test_welch_tables_identity():
+    from localmd_b200._tables import welch_from_tables_reference, welch_tables
+
+    tc, ts = welch_tables()
+    assert tc.shape == (128, 64) and ts.shape == (128, 64) and tc.dtype == np.float32
+    rng = np.random.default_rng(0)
+    for n in (1024, 544, 256, 300):
+        x = (200 + 3 * rng.standard_normal((16, n))).astype(np.float32)
+        np.testing.assert_allclose(welch_from_tables_reference(x), O.welch_noise_estimate(x), rtol=1e-6)
+
+
+def test_npz_layout_and_pmdarray_container():
+    import localmd_b200
+
+    rng = np.random.default_rng(0)
+    d1, d2, T, R, k = 6, 5, 20, 7, 4
+    u = sp.random(d1 * d2, R, density=0.4, random_state=1, format="csr")
+    arr = localmd_b200.PMDArray(u.tocoo(), rng.standard_normal((R, k)).astype(np.float32), np.array([4, 3, 2, 1], np.float32),
+                                rng.standard_normal((k, T)).astype(np.float32), (T, d1, d2), "F", np.ones((d1, d2), np.float32),
+                                np.ones((d1, d2), np.float32))
+    assert arr.shape == (T, d1, d2) and arr.ndim == 3 and arr.dtype == np.float32 and sp.isspmatrix_csr(arr.u)
+    np.testing.assert_array_equal(arr.row_indices, np.arange(30).reshape((6, 5), order="F"))
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "x.npz")
+        localmd_b200.save_npz(path, arr)
+        data = np.load(path, allow_pickle=True)
+        assert sorted(data.files) == sorted(["fov_shape", "fov_order", "U_data", "U_indices", "U_indptr", "U_shape", "U_format",
+                                             "R", "s", "Vt", "mean_img", "noise_var_img"])
+        assert tuple(data["fov_shape"]) == (d1, d2) and data["fov_order"].item() == "F"
+        back = localmd_b200.load_npz(path)
+        assert back.shape == arr.shape and (back.u != arr.u).nnz == 0
+        np.testing.assert_array_equal(back.v, arr.v)
+    for bad in [None, (None, 1, 2), (1, 2, 3, 4)]:
+        with pytest.raises(ValueError):
+            arr[bad]
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_fails_loudly_without_cuda():
+    import localmd_b200
+
+    movie = np.zeros((300, 20, 20), np.float32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        localmd_b200.localmd_decomposition(movie, [16, 16], 100)
+    arr = localmd_b200.PMDArray(sp.eye(400, 3, format="csr"), np.eye(3, dtype=np.float32), np.ones(3, np.float32),
+                                np.ones((3, 300), np.float32), (300, 20, 20), "F", np.zeros((20, 20), np.float32),
+                                np.ones((20, 20), np.float32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        arr[0]
+
+
+def test_lazy_data_loader_contract():
+    import localmd_b200
+
+    data = np.arange(10 * 4 * 3, dtype=np.float32).reshape(10, 4, 3)
+
+    class Arr(localmd_b200.lazy_data_loader):
+        dtype = "float32"
+        shape = data.shape
+
+        def _compute_at_indices(self, idx):
+            return data[idx]
+
+    a = Arr()
+    np.testing.assert_array_equal(a[[1, 3]], data[[1, 3]])
+    np.testing.assert_array_equal(a[2], data[2])
+    np.testing.assert_array_equal(a[2:5, 1], data[2:5, 1])
+    np.testing.assert_array_equal(a[np.array([0, 9]), :, 2], data[[0, 9], :, 2])
+    with pytest.raises(IndexError):
+        a[0, 0, 0, 0]
+    with pytest.raises(IndexError):
+        a[0:11]
+    with pytest.raises(IndexError):
+        a["x"]

@@ -263,6 +263,37 @@ def test_project_local_and_dense(ops, bh, bw, max_rank, dtype):
     assert np.all(got[:, T:] == np.where(np.arange(n_local + K)[:, None] < n_local, 0.0 if bh * bw > 512 else 7.0, 0.0))
 
 
+@pytest.mark.parametrize(
+    "bh,bw,max_rank,dtype,d1,d2",
+    [(10, 10, 3, np.float32, 61, 83), (16, 16, 9, np.uint16, 61, 83), (20, 20, 5, np.float32, 112, 95), (22, 22, 13, np.int16, 61, 83),
+     (20, 12, 6, np.float32, 64, 40), (20, 20, 2, np.float64, 20, 20)],
+)
+def test_project_supertile(ops, bh, bw, max_rank, dtype, d1, d2):
+    rng = np.random.default_rng(bh * 3 + max_rank)
+    T, K = 1100, 1
+    starts, ranks, col0, uv, bg, U = _random_sparse_u(rng, d1, d2, bh, bw, max_rank, K)
+    y = rng.uniform(0, 200, size=(T, d1 * d2))
+    movie = (np.rint(y) if np.issubdtype(dtype, np.integer) else y).astype(dtype)
+    mean = rng.uniform(80, 120, d1 * d2).astype(np.float32)
+    std = rng.uniform(0.5, 2, d1 * d2).astype(np.float32)
+    inv = (1.0 / std).astype(np.float32)
+    n_local = int(ranks.sum())
+    st = ops.make_supertiles(O.tile_starts(d1, bh), O.tile_starts(d2, bw), bh, bw, ranks, col0)
+    std_ = {k: (dev(v) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+    z = torch.full((n_local, T + 5), 7.0, dtype=torch.float32, device="cuda")
+    ops.project_supertile(dev(movie), d2, std_, bh, bw, dev(uv), dev(mean), dev(inv), z)
+    yc = (movie.astype(np.float32).astype(np.float64) - mean) / std
+    ref = (U.T @ yc.T)[:n_local]
+    got = z.cpu().numpy()
+    np.testing.assert_allclose(got[:, :T], ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+    assert np.all(got[:, T:] == 7.0)  # nothing written beyond the movie
+    z2 = torch.zeros((n_local, T), dtype=torch.float32, device="cuda")
+    if dtype == np.float32:
+        ops.project_supertile(dev(movie), d2, std_, bh, bw, dev(uv), None, None, z2)
+        ref2 = (U.T @ movie.astype(np.float64).T)[:n_local]
+        np.testing.assert_allclose(z2.cpu().numpy(), ref2, rtol=0, atol=2e-5 * np.abs(ref2).max())
+
+
 def test_project_without_standardisation(ops):
     rng = np.random.default_rng(9)
     d1, d2, T, K, bh, bw = 40, 36, 50, 2, 16, 16

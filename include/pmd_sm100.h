@@ -72,11 +72,19 @@ int pmd_gram_f64(const float* a, int64_t batch, int64_t n, int64_t m_len, int64_
  *           pmd_loader.py:60. */
 int pmd_jacobi_eigh(double* c, int64_t batch, int64_t n, int mode, double* w, float* vecs, void* stream);
 
+/* gather + standardise + TRANSPOSE frames into the pixel-major init movie used by the block stage:
+ *   out[p*ld + i] = (movie[frames[i]][p] - mean[p]) / stdv[p]   (i < n_frames; columns n_frames..ld-1 are zeroed)
+ * replaces: pmd_loader.py:348-371 (temporal_crop_with_filter's frame loads) + 374-377.  ld >= n_frames, a
+ * multiple of 4 (16-byte rows). */
+int pmd_standardize_frames_t(const void* movie, int dtype, int64_t d, const int64_t* frames, int64_t n_frames,
+                             const float* mean, const float* stdv, float* out, int64_t ld, void* stream);
+
 /* 2x2(-ish) average pooling + temporal averaging of every block of the standardised init movie.
  * replaces: decomposition.py:192-232 (downsample_average_pooling) + 283-290.
- * yres: [t][d] float32.  starts: [nb][2] int32 (i0, j0).  Output bta [nb][t/taf][P] float32 with
+ * yt: pixel-major init movie [d][ld] float32 (frame f of pixel p at yt[p*ld+f]), t frames used.
+ * starts: [nb][2] int32 (i0, j0).  Output bta [nb][P][t/taf] float32 with
  * P = ceil(bh/saf)*ceil(bw/saf), pooled pixel index pi*ceil(bw/saf)+pj, XLA 'SAME' padding. */
-int pmd_block_pool_tavg(const float* yres, int64_t t, int64_t d2, int64_t d, const int32_t* starts, int64_t nb,
+int pmd_block_pool_tavg(const float* yt, int64_t ld, int64_t t, int64_t d2, const int32_t* starts, int64_t nb,
                         int64_t bh, int64_t bw, int64_t saf, int64_t taf, float* bta, void* stream);
 
 /* spread a pooled spatial basis back to full resolution: w[b][q][c] = uds[b][pool(q)][c] / count(pool(q)),
@@ -85,29 +93,30 @@ int pmd_block_pool_tavg(const float* yres, int64_t t, int64_t d2, int64_t d, con
 int pmd_block_unpool(const float* uds, int64_t nb, int64_t bh, int64_t bw, int64_t saf, int64_t r, int64_t rp,
                      float* w, void* stream);
 
-/* streaming block projection  out[b][c][f] = sum_q w[b][q][c] * Y_b[q][f]   (c < r, f < t).
+/* streaming block projection  out[b][c][f] = sum_q w[b][q][c] * Y_b[q][f]   (c < r, f < ldo).
  * replaces: decomposition.py:295-298 (u^T * pooled block), 318 (u_final^T * block), 390-407.
- * movie: float32 [t][d] (+ b*movie_batch_stride elements for block b: 0 = all blocks share one movie,
- * used by the threshold simulation where every "block" is its own tiny movie).
- * w: [nb][bh*bw][rp]; out: [nb][r][t]. */
-int pmd_block_project(const float* movie, int64_t movie_batch_stride, int64_t t, int64_t d2, int64_t d,
+ * movie_t: pixel-major float32 [d][ld] (+ b*movie_batch_stride elements for block b: 0 = all blocks share one
+ * movie; non-zero is used by the threshold simulation where every "block" is its own tiny movie).  ld is a
+ * multiple of 4 and columns t..ld-1 hold zeros.  w: [nb][bh*bw][rp]; out: [nb][r][ldo], ldo <= ld. */
+int pmd_block_project(const float* movie_t, int64_t movie_batch_stride, int64_t ld, int64_t d2,
                       const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* w, int64_t r,
-                      int64_t rp, float* out, void* stream);
+                      int64_t rp, float* out, int64_t ldo, void* stream);
 
-/* streaming spatial projection  s[b][q][c] = sum_f Y_b[q][f] * vb[b][c][f].
- * replaces: decomposition.py:304-306 (block * v_basis^T).   vb: [nb][r][t]; s: [nb][bh*bw][rp]. */
-int pmd_block_spatial(const float* movie, int64_t movie_batch_stride, int64_t t, int64_t d2, int64_t d,
-                      const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* vb, int64_t r,
-                      int64_t rp, float* s, void* stream);
+/* streaming spatial projection  s[b][q][c] = sum_f Y_b[q][f] * v[b][c][f]   (all ldv frames of v).
+ * replaces: decomposition.py:304-306 (block * v_basis^T).   v: [nb][r][ldv] (ldv multiple of 4, padding
+ * zero); s: [nb][bh*bw][rp], rp <= 64. */
+int pmd_block_spatial(const float* movie_t, int64_t movie_batch_stride, int64_t ld, int64_t d2,
+                      const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* v, int64_t ldv,
+                      int64_t r, int64_t rp, float* s, void* stream);
 
 /* roughness statistics of every component of every block + the keep-through-first-failure rule.
  * replaces: evaluation.py:84-126 (spatial/temporal_roughness_stat), 133-192, 195-222
  *           (filter_by_failures) and decomposition.py:502-506.
- * u: [nb][bh*bw][rp] spatial components, v: [nb][r][t] temporal components.
+ * u: [nb][bh*bw][rp] spatial components, v: [nb][r][ldv] temporal components (first t columns used).
  * Outputs: sstat, tstat [nb][r] float32; ranks [nb] int32 (number of kept leading components). */
 int pmd_block_stats_rank(const float* u, const float* v, int64_t nb, int64_t bh, int64_t bw, int64_t r,
-                         int64_t rp, int64_t t, float thr_s, float thr_t, int64_t max_fail, float* sstat,
-                         float* tstat, int32_t* ranks, void* stream);
+                         int64_t rp, int64_t t, int64_t ldv, float thr_s, float thr_t, int64_t max_fail,
+                         float* sstat, float* tstat, int32_t* ranks, void* stream);
 
 /* weighted assembly of the sparse spatial matrix in block-component form.
  * replaces: decomposition.py:811-853 (pyramid weighting, COO construction, division by the summed
@@ -142,6 +151,24 @@ int pmd_project_supertile(const void* movie, int dtype, int64_t t, int64_t d2, i
                           int64_t max_region_h, int64_t max_region_w, const float* uvals32, const float* mean,
                           const float* inv_std, float* z, int64_t ldz, void* stream);
 
+/* K7 (v3)  the whole projection  z = U^T ((Y - mean) * inv_std)  in ONE streaming pass over the movie: local
+ * (block-supported) and dense background columns together.  A CTA walks a column strip of the field of view
+ * (all rows, <= 48 pixels wide) for 256 frames, one pixel row at a time; its 8 warps own "tasks" packed into
+ * slots by the host (localmd_b200/ops.py: make_strips):
+ *   items:    [n_items][8] int32  = (c0, rw, first slot_ptr entry, n_rows, bg partial index, first row, 0, 0)
+ *   slot_ptr: 9 consecutive int32 per item: tasks of warp w are slot_ptr[first+w] .. slot_ptr[first+w+1]-1
+ *   tasks:    [n_tasks][12] int32 = (first row, column offset in the strip, rows, width, output column,
+ *             number of components 1..8, padded components 4|8, floats per row of its U pack, U pack offset
+ *             (low, high 32 bits), kind 0 local | 1 background, 0), row ranges of one slot disjoint, ascending
+ *   upack:    float32 U values per task as [row][pixel][padded component] (zero padded)
+ * Local tasks write z[col..col+nc) (every element once); background tasks write the partial sums of their
+ * strip to zbg[bg partial][component][frame] (the caller adds the partials).  mean / inv_std may be NULL.
+ * replaces: pmd_loader.py:316-346, 392-414 (v_projection / v_projection_routine) in full. */
+int pmd_project_stream(const void* movie, int dtype, int64_t t, int64_t d2, int64_t d, const int32_t* items,
+                       int64_t n_items, const int32_t* slot_ptr, const int32_t* tasks, int64_t max_rw,
+                       const float* upack, const float* mean, const float* inv_std, float* z, int64_t ldz,
+                       float* zbg, int64_t ldzbg, int64_t bg_stride, void* stream);
+
 /* K7b  full-movie projection onto dense (background) columns:
  *   z[c][f] += sum_p basis[c][p] * (movie[f][p] - mean[p]) * inv_std[p]     (c < k <= 16)
  * replaces: the same v_projection for the dense background columns appended at
@@ -168,6 +195,17 @@ int pmd_reconstruct_f64(const int64_t* indptr, const int32_t* indices, const dou
 int pmd_project_cols_f64(const double* w, int64_t m, int64_t d2, int64_t d, const int32_t* starts, int64_t bh,
                          int64_t bw, const int32_t* blk_of_col, const int64_t* col0, int64_t n_local,
                          const double* uvals64, const double* bg64, int64_t n_cols, double* z, void* stream);
+
+/* block-sparse Gram of the local columns of U (float64), written directly as canonical CSR:
+ * for every ordered pair p = (b1, b2) of blocks whose windows overlap, the dense tile
+ *   G[c1][c2] = sum over the overlap of  uvals64[col0[b1]+c1][.] * uvals64[col0[b2]+c2][.]
+ * goes to vals[rowptr[col0[b1]+c1] + pair_rowoff[p] + c2] with column id col0[b2]+c2 in cols[...].
+ * replaces: the scipy.sparse product u.T.dot(u) implied by decomposition.py:974-981.
+ * pairs [n_pairs][2] int32 sorted by (b1, b2); pair_rowoff[p] = number of entries that precede tile p in each of
+ * its rows; rowptr [n_local+1] (all built by the host from ranks, localmd_b200/decomposition.py: SparseU.gram). */
+int pmd_utu_pairs(const int32_t* pairs, int64_t n_pairs, const int64_t* pair_rowoff, const int32_t* starts,
+                  int64_t bh, int64_t bw, const int32_t* ranks, const int64_t* col0, const double* uvals64,
+                  const int64_t* rowptr, double* vals, int32_t* cols, void* stream);
 
 #ifdef __cplusplus
 }

@@ -21,36 +21,6 @@ __host__ __device__ inline PoolGeom pool_geom(int bh, int bw, int saf) {
     return g;
 }
 
-constexpr int kPoolTau = 8;
-
-__global__ void __launch_bounds__(128)
-block_pool_tavg_kernel(const float* __restrict__ yres, int64_t t, int64_t d2, int64_t d, const int32_t* __restrict__ starts,
-                       int bh, int bw, int saf, int taf, float* __restrict__ bta) {
-    const PoolGeom g = pool_geom(bh, bw, saf);
-    const int P = g.ph * g.pw;
-    const int64_t tp = t / taf;
-    const int64_t b = blockIdx.y;
-    const int i0 = starts[2 * b], j0 = starts[2 * b + 1];
-    const int64_t tau0 = (int64_t)blockIdx.x * kPoolTau;
-    for (int p = threadIdx.x; p < P; p += blockDim.x) {
-        const int pi = p / g.pw, pj = p % g.pw;
-        const int r0 = max(pi * saf - g.lo_h, 0), r1 = min(pi * saf - g.lo_h + saf, bh);
-        const int c0 = max(pj * saf - g.lo_w, 0), c1 = min(pj * saf - g.lo_w + saf, bw);
-        const float cnt = (float)((r1 - r0) * (c1 - c0));
-        for (int64_t tau = tau0; tau < min(tau0 + kPoolTau, tp); ++tau) {
-            float acc = 0.f;
-            for (int ff = 0; ff < taf; ++ff) {
-                const float* fr = yres + (tau * taf + ff) * d + (int64_t)i0 * d2 + j0;
-                float sum = 0.f;
-                for (int r = r0; r < r1; ++r)
-                    for (int c = c0; c < c1; ++c) sum += fr[(int64_t)r * d2 + c];
-                acc += sum / cnt;
-            }
-            bta[(b * tp + tau) * P + p] = acc / (float)taf;
-        }
-    }
-}
-
 __global__ void block_unpool_kernel(const float* __restrict__ uds, int64_t nb, int bh, int bw, int saf, int r, int rp,
                                     float* __restrict__ w) {
     const PoolGeom g = pool_geom(bh, bw, saf);
@@ -71,143 +41,6 @@ __global__ void block_unpool_kernel(const float* __restrict__ uds, int64_t nb, i
             v = uds[(b * P + pi * g.pw + pj) * r + c] / (float)((r1 - r0) * (c1 - c0));
         }
         w[idx] = v;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// out[b][c][f] = sum_q w[b][q][c] * Y_b[q][f]       (SGEMM-style: 4 comps x 4 frames per thread,
-// pixel chunks of 64 staged through shared memory; threads = 16 frame groups x rp/4 comp groups)
-// ------------------------------------------------------------------------------------------------
-constexpr int kProjFT = 64;   // frames per CTA
-constexpr int kProjKC = 64;   // pixels per staged chunk
-constexpr int kProjLd = kProjFT + 4;
-
-__global__ void block_project_kernel(const float* __restrict__ movie, int64_t mbs, int64_t t, int64_t d2, int64_t d,
-                                     const int32_t* __restrict__ starts, int bh, int bw, const float* __restrict__ w,
-                                     int r, int rp, float* __restrict__ out) {
-    extern __shared__ __align__(16) float psm[];
-    float* wch = psm;                     // [kProjKC][rp]
-    float* tile = psm + kProjKC * rp;     // [kProjKC][kProjLd]
-    const int nthreads = blockDim.x;
-    const int tid = threadIdx.x;
-    const int ncg = rp / 4;
-    const int cg = tid % ncg, fg = tid / ncg;
-    const int64_t b = blockIdx.y;
-    const int64_t f0 = (int64_t)blockIdx.x * kProjFT;
-    const int i0 = starts[2 * b], j0 = starts[2 * b + 1];
-    const int bpix = bh * bw;
-    const float* mv = movie + b * mbs + (int64_t)i0 * d2 + j0;
-    const float* wb = w + b * (int64_t)bpix * rp;
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-
-    for (int q0 = 0; q0 < bpix; q0 += kProjKC) {
-        const int kc = min(kProjKC, bpix - q0);
-        for (int idx = tid; idx < kc * rp; idx += nthreads) wch[idx] = wb[(int64_t)q0 * rp + idx];
-        for (int idx = tid; idx < kProjKC * kProjFT; idx += nthreads) {
-            const int ff = idx / kProjKC, qq = idx % kProjKC;
-            float v = 0.f;
-            if (qq < kc && f0 + ff < t) {
-                const int q = q0 + qq;
-                const int qi = q / bw, qj = q - qi * bw;
-                v = mv[(f0 + ff) * d + (int64_t)qi * d2 + qj];
-            }
-            tile[qq * kProjLd + ff] = v;
-        }
-        __syncthreads();
-        for (int qq = 0; qq < kc; ++qq) {
-            const float4 wv = *reinterpret_cast<const float4*>(&wch[qq * rp + cg * 4]);
-            const float4 xv = *reinterpret_cast<const float4*>(&tile[qq * kProjLd + fg * 4]);
-            const float wa[4] = {wv.x, wv.y, wv.z, wv.w};
-            const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(wa[i], xa[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int c = cg * 4 + i;
-        if (c >= r) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int64_t f = f0 + fg * 4 + j;
-            if (f < t) out[(b * r + c) * t + f] = acc[i][j];
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// s[b][q][c] = sum_f Y_b[q][f] * vb[b][c][f]        (64 pixels x rp comps per CTA, loop over time)
-// ------------------------------------------------------------------------------------------------
-constexpr int kSpatPT = 64;
-constexpr int kSpatFC = 32;
-
-__global__ void block_spatial_kernel(const float* __restrict__ movie, int64_t mbs, int64_t t, int64_t d2, int64_t d,
-                                     const int32_t* __restrict__ starts, int bh, int bw, const float* __restrict__ vb,
-                                     int r, int rp, float* __restrict__ s) {
-    extern __shared__ __align__(16) float ssm[];
-    float* tileT = ssm;                          // [kSpatFC][kSpatPT]
-    float* vbT = ssm + kSpatFC * kSpatPT;        // [kSpatFC][rp]
-    int* pixoff = reinterpret_cast<int*>(vbT + kSpatFC * rp);  // [kSpatPT]
-    const int nthreads = blockDim.x;
-    const int tid = threadIdx.x;
-    const int ncg = rp / 4;
-    const int cg = tid % ncg, pg = tid / ncg;
-    const int64_t b = blockIdx.y;
-    const int q0 = blockIdx.x * kSpatPT;
-    const int i0 = starts[2 * b], j0 = starts[2 * b + 1];
-    const int bpix = bh * bw;
-    const float* mv = movie + b * mbs;
-    for (int qq = tid; qq < kSpatPT; qq += nthreads) {
-        const int q = q0 + qq;
-        int off = -1;
-        if (q < bpix) {
-            const int qi = q / bw, qj = q - qi * bw;
-            off = (i0 + qi) * (int)d2 + j0 + qj;
-        }
-        pixoff[qq] = off;
-    }
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    __syncthreads();
-    for (int64_t fc = 0; fc < t; fc += kSpatFC) {
-        for (int idx = tid; idx < kSpatFC * kSpatPT; idx += nthreads) {
-            const int ff = idx / kSpatPT, qq = idx % kSpatPT;
-            const int off = pixoff[qq];
-            tileT[idx] = (off >= 0 && fc + ff < t) ? mv[(fc + ff) * d + off] : 0.f;
-        }
-        for (int idx = tid; idx < rp * kSpatFC; idx += nthreads) {
-            const int c = idx / kSpatFC, ff = idx % kSpatFC;
-            vbT[ff * rp + c] = (c < r && fc + ff < t) ? vb[(b * r + c) * t + fc + ff] : 0.f;
-        }
-        __syncthreads();
-#pragma unroll 4
-        for (int ff = 0; ff < kSpatFC; ++ff) {
-            const float4 xv = *reinterpret_cast<const float4*>(&tileT[ff * kSpatPT + pg * 4]);
-            const float4 vv = *reinterpret_cast<const float4*>(&vbT[ff * rp + cg * 4]);
-            const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
-            const float va[4] = {vv.x, vv.y, vv.z, vv.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xa[i], va[j], acc[i][j]);
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int q = q0 + pg * 4 + i;
-        if (q >= bpix) continue;
-        *reinterpret_cast<float4*>(&s[(b * bpix + q) * rp + cg * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
     }
 }
 
@@ -235,12 +68,12 @@ __global__ void spatial_stat_kernel(const float* __restrict__ u, int bh, int bw,
     }
 }
 
-__global__ void __launch_bounds__(128) temporal_stat_kernel(const float* __restrict__ v, int64_t nrows, int64_t t,
+__global__ void __launch_bounds__(128) temporal_stat_kernel(const float* __restrict__ v, int64_t nrows, int64_t t, int64_t ldv,
                                                             float* __restrict__ tstat) {
     const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= nrows) return;
     const int lane = threadIdx.x & 31;
-    const float* vr = v + row * t;
+    const float* vr = v + row * ldv;
     double sd = 0.0, sa = 0.0;
     for (int64_t i = lane; i < t; i += 32) {
         const float m = vr[i];
@@ -295,18 +128,6 @@ __global__ void assemble_u_kernel(const float* __restrict__ u, int bh, int bw, i
 }  // namespace pmd
 
 // =================================================================================================
-extern "C" int pmd_block_pool_tavg(const float* yres, int64_t t, int64_t d2, int64_t d, const int32_t* starts,
-                                   int64_t nb, int64_t bh, int64_t bw, int64_t saf, int64_t taf, float* bta, void* stream) {
-    const char* fn = "pmd_block_pool_tavg";
-    PMD_REQUIRE(yres && starts && bta, fn, "null pointer");
-    PMD_REQUIRE(t > 0 && nb > 0 && nb <= 65535 && bh > 0 && bw > 0 && saf > 0 && taf > 0 && t / taf > 0, fn, "bad size");
-    const int64_t tp = t / taf;
-    dim3 grid((unsigned)((tp + pmd::kPoolTau - 1) / pmd::kPoolTau), (unsigned)nb);
-    pmd::block_pool_tavg_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(yres, t, d2, d, starts, (int)bh, (int)bw, (int)saf,
-                                                                       (int)taf, bta);
-    return pmd::check_launch(fn);
-}
-
 extern "C" int pmd_block_unpool(const float* uds, int64_t nb, int64_t bh, int64_t bw, int64_t saf, int64_t r, int64_t rp,
                                 float* w, void* stream) {
     const char* fn = "pmd_block_unpool";
@@ -318,48 +139,16 @@ extern "C" int pmd_block_unpool(const float* uds, int64_t nb, int64_t bh, int64_
     return pmd::check_launch(fn);
 }
 
-extern "C" int pmd_block_project(const float* movie, int64_t movie_batch_stride, int64_t t, int64_t d2, int64_t d,
-                                 const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* w, int64_t r,
-                                 int64_t rp, float* out, void* stream) {
-    const char* fn = "pmd_block_project";
-    PMD_REQUIRE(movie && starts && w && out, fn, "null pointer");
-    PMD_REQUIRE(t > 0 && nb > 0 && nb <= 65535 && r > 0 && rp >= r && rp % 4 == 0 && rp <= 128, fn, "bad size");
-    const int threads = 16 * (int)(rp / 4);
-    const size_t smem = (size_t)(pmd::kProjKC * rp + pmd::kProjKC * pmd::kProjLd) * sizeof(float);
-    cudaError_t e = cudaFuncSetAttribute(pmd::block_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
-    dim3 grid((unsigned)((t + pmd::kProjFT - 1) / pmd::kProjFT), (unsigned)nb);
-    pmd::block_project_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(movie, movie_batch_stride, t, d2, d, starts,
-                                                                             (int)bh, (int)bw, w, (int)r, (int)rp, out);
-    return pmd::check_launch(fn);
-}
-
-extern "C" int pmd_block_spatial(const float* movie, int64_t movie_batch_stride, int64_t t, int64_t d2, int64_t d,
-                                 const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* vb, int64_t r,
-                                 int64_t rp, float* s, void* stream) {
-    const char* fn = "pmd_block_spatial";
-    PMD_REQUIRE(movie && starts && vb && s, fn, "null pointer");
-    PMD_REQUIRE(t > 0 && nb > 0 && nb <= 65535 && r > 0 && rp >= r && rp % 4 == 0 && rp <= 128, fn, "bad size");
-    const int threads = 16 * (int)(rp / 4);
-    const size_t smem = (size_t)(pmd::kSpatFC * pmd::kSpatPT + pmd::kSpatFC * rp) * sizeof(float) + pmd::kSpatPT * sizeof(int);
-    cudaError_t e = cudaFuncSetAttribute(pmd::block_spatial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
-    dim3 grid((unsigned)((bh * bw + pmd::kSpatPT - 1) / pmd::kSpatPT), (unsigned)nb);
-    pmd::block_spatial_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(movie, movie_batch_stride, t, d2, d, starts,
-                                                                             (int)bh, (int)bw, vb, (int)r, (int)rp, s);
-    return pmd::check_launch(fn);
-}
-
 extern "C" int pmd_block_stats_rank(const float* u, const float* v, int64_t nb, int64_t bh, int64_t bw, int64_t r,
-                                    int64_t rp, int64_t t, float thr_s, float thr_t, int64_t max_fail, float* sstat,
-                                    float* tstat, int32_t* ranks, void* stream) {
+                                    int64_t rp, int64_t t, int64_t ldv, float thr_s, float thr_t, int64_t max_fail,
+                                    float* sstat, float* tstat, int32_t* ranks, void* stream) {
     const char* fn = "pmd_block_stats_rank";
     PMD_REQUIRE(u && v && sstat && tstat && ranks, fn, "null pointer");
-    PMD_REQUIRE(nb > 0 && r > 0 && rp >= r && t > 2 && max_fail >= 1 && bh > 1 && bw > 1, fn, "bad size");
+    PMD_REQUIRE(nb > 0 && r > 0 && rp >= r && t > 2 && ldv >= t && max_fail >= 1 && bh > 1 && bw > 1, fn, "bad size");
     cudaStream_t st = (cudaStream_t)stream;
     pmd::spatial_stat_kernel<<<(unsigned)nb, 64, 0, st>>>(u, (int)bh, (int)bw, (int)r, (int)rp, sstat);
     const int64_t nrows = nb * r;
-    pmd::temporal_stat_kernel<<<(unsigned)((nrows + 3) / 4), 128, 0, st>>>(v, nrows, t, tstat);
+    pmd::temporal_stat_kernel<<<(unsigned)((nrows + 3) / 4), 128, 0, st>>>(v, nrows, t, ldv, tstat);
     pmd::rank_select_kernel<<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(sstat, tstat, nb, (int)r, thr_s, thr_t, (int)max_fail,
                                                                           ranks);
     return pmd::check_launch(fn);

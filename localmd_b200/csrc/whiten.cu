@@ -1,0 +1,50 @@
+// Sparse Gram of the local columns of U for the whitening step  G = M^T (U^T U) M
+// (decomposition.py:974-996).  The reference forms U^T U with scipy.sparse on the host; here the
+// block structure is used directly: two local columns interact only when their block windows
+// overlap, so U^T U restricted to the local columns is a block-sparse matrix with one dense
+// rank(b1) x rank(b2) tile per ordered pair of overlapping blocks.  One CTA per pair, float64.
+#include "common.cuh"
+
+namespace pmd {
+
+__global__ void __launch_bounds__(128)
+utu_pairs_kernel(const int32_t* __restrict__ pairs, const int64_t* __restrict__ pair_rowoff, const int32_t* __restrict__ starts,
+                 int bh, int bw, const int32_t* __restrict__ ranks, const int64_t* __restrict__ col0,
+                 const double* __restrict__ uvals, const int64_t* __restrict__ rowptr, double* __restrict__ vals,
+                 int32_t* __restrict__ cols) {
+    const int64_t p = blockIdx.x;
+    const int b1 = pairs[2 * p], b2 = pairs[2 * p + 1];
+    const int r1 = ranks[b1], r2 = ranks[b2];
+    const int i1 = starts[2 * b1], j1 = starts[2 * b1 + 1], i2 = starts[2 * b2], j2 = starts[2 * b2 + 1];
+    const int ilo = max(i1, i2), ihi = min(i1, i2) + bh, jlo = max(j1, j2), jhi = min(j1, j2) + bw;
+    const int bpix = bh * bw;
+    const int64_t c01 = col0[b1], c02 = col0[b2];
+    const int64_t ro = pair_rowoff[p];
+    for (int idx = threadIdx.x; idx < r1 * r2; idx += blockDim.x) {
+        const int c1 = idx / r2, c2 = idx - c1 * r2;
+        const double* u1 = uvals + (c01 + c1) * bpix;
+        const double* u2 = uvals + (c02 + c2) * bpix;
+        double acc = 0.0;
+        for (int i = ilo; i < ihi; ++i) {
+            const double* a = u1 + (i - i1) * bw - j1;
+            const double* b = u2 + (i - i2) * bw - j2;
+            for (int j = jlo; j < jhi; ++j) acc = fma(a[j], b[j], acc);
+        }
+        const int64_t pos = rowptr[c01 + c1] + ro + c2;
+        vals[pos] = acc;
+        cols[pos] = (int32_t)(c02 + c2);
+    }
+}
+
+}  // namespace pmd
+
+extern "C" int pmd_utu_pairs(const int32_t* pairs, int64_t n_pairs, const int64_t* pair_rowoff, const int32_t* starts,
+                             int64_t bh, int64_t bw, const int32_t* ranks, const int64_t* col0, const double* uvals64,
+                             const int64_t* rowptr, double* vals, int32_t* cols, void* stream) {
+    const char* fn = "pmd_utu_pairs";
+    PMD_REQUIRE(pairs && pair_rowoff && starts && ranks && col0 && uvals64 && rowptr && vals && cols, fn, "null pointer");
+    PMD_REQUIRE(n_pairs > 0 && n_pairs < ((int64_t)1 << 31) && bh > 0 && bw > 0, fn, "bad size");
+    pmd::utu_pairs_kernel<<<(unsigned)n_pairs, 128, 0, (cudaStream_t)stream>>>(pairs, pair_rowoff, starts, (int)bh, (int)bw, ranks,
+                                                                              col0, uvals64, rowptr, vals, cols);
+    return pmd::check_launch(fn);
+}

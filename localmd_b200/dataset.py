@@ -125,12 +125,17 @@ class DeviceMovie:
     """The movie as the kernels see it: frame-major (T, d) on one GPU.
 
     * a CUDA torch tensor (T, d1, d2) of a supported dtype is used in place (zero copy);
-    * anything else honouring the dataset contract is staged through pinned host buffers: kept
-      resident in HBM when it fits `resident_fraction` of the free memory, otherwise re-streamed
-      batch by batch for each of the two full passes.
+    * anything else honouring the dataset contract is moved host -> device in `upload_frames`-sized
+      chunks on a side stream.  When it fits `resident_fraction` of the free memory it is kept in HBM:
+      the FIRST call of batches() (the mean/noise pass) performs the upload and hands every chunk to the
+      compute stream as soon as it has landed, so the copy overlaps that pass; later passes read HBM.
+      Otherwise every pass re-streams the movie chunk by chunk.
+    Contiguous ndarrays / CPU tensors of a native dtype are sliced without a host copy (pinned memory is
+    copied from directly, pageable memory goes through two reusable pinned staging buffers).
     frame_lo/frame_hi restrict the wrapper to a frame shard (multi-GPU)."""
 
-    def __init__(self, dataset_obj, device, batch_frames=2048, frame_lo=0, frame_hi=None, resident_fraction=0.6):
+    def __init__(self, dataset_obj, device, batch_frames=2048, frame_lo=0, frame_hi=None, resident_fraction=0.6,
+                 upload_frames=2048):
         self.device = torch.device(device)
         self.T_total = int(dataset_obj.shape[0])
         self.d1, self.d2 = int(dataset_obj.shape[1]), int(dataset_obj.shape[2])
@@ -138,13 +143,20 @@ class DeviceMovie:
         self.lo = int(frame_lo)
         self.hi = self.T_total if frame_hi is None else int(frame_hi)
         self.batch_frames = max(1024, (int(batch_frames) // 1024) * 1024)
+        self.upload_frames = max(1024, (int(upload_frames) // 1024) * 1024)
         self.h2d_bytes = 0
         self._src = dataset_obj
         self._resident = None
+        self._filled = True
+        self._host2d = None
+        self._staging = None
         if isinstance(dataset_obj, torch.Tensor):
             if not dataset_obj.is_cuda:
-                dataset_obj = dataset_obj.numpy()
-                self._src = dataset_obj
+                if dataset_obj.dtype in ops.PMD_DTYPES and dataset_obj.is_contiguous():
+                    self._host2d = dataset_obj.view(self.T_total, self.d)
+                else:
+                    dataset_obj = dataset_obj.numpy()
+                    self._src = dataset_obj
             else:
                 t = dataset_obj
                 if t.dtype not in ops.PMD_DTYPES:
@@ -152,17 +164,24 @@ class DeviceMovie:
                 self._resident = t[self.lo : self.hi].contiguous().view(self.hi - self.lo, self.d)
                 self.torch_dtype = t.dtype
                 return
-        probe = np.asarray(self._src[[self.lo]])
-        self._np_native = probe.dtype in ops.NUMPY_NATIVE
-        self.torch_dtype = ops.NUMPY_NATIVE[probe.dtype] if self._np_native else torch.float32
+        if self._host2d is None and isinstance(self._src, np.ndarray) and self._src.dtype in ops.NUMPY_NATIVE \
+                and self._src.flags.c_contiguous:
+            self._host2d = torch.from_numpy(self._src).view(self.T_total, self.d)
+        if self._host2d is not None:
+            self._np_native = True
+            self.torch_dtype = self._host2d.dtype
+            self._pinned_src = bool(self._host2d.is_pinned())
+        else:
+            probe = np.asarray(self._src[[self.lo]])
+            self._np_native = probe.dtype in ops.NUMPY_NATIVE
+            self.torch_dtype = ops.NUMPY_NATIVE[probe.dtype] if self._np_native else torch.float32
+            self._pinned_src = False
+        self._copy_stream = torch.cuda.Stream(self.device)
         nbytes = (self.hi - self.lo) * self.d * torch.empty((), dtype=self.torch_dtype).element_size()
         free, _ = torch.cuda.mem_get_info(self.device)
         if nbytes <= resident_fraction * free:
-            buf = torch.empty((self.hi - self.lo, self.d), dtype=self.torch_dtype, device=self.device)
-            for f0, f1, chunk in self._host_batches():
-                buf[f0 - self.lo : f1 - self.lo].copy_(chunk, non_blocking=True)
-            torch.cuda.current_stream(self.device).synchronize()
-            self._resident = buf
+            self._resident = torch.empty((self.hi - self.lo, self.d), dtype=self.torch_dtype, device=self.device)
+            self._filled = False
 
     @property
     def n_local(self):
@@ -172,7 +191,9 @@ class DeviceMovie:
     def shape(self):
         return (self.T_total, self.d1, self.d2)
 
+    # ---- host side ---------------------------------------------------------------------------------
     def _host_frames(self, ids):
+        """Pinned (n, d) host tensor of arbitrary frames through the dataset contract."""
         arr = np.asarray(self._src[list(ids)])
         if arr.ndim == 2:
             arr = arr[None]
@@ -180,31 +201,107 @@ class DeviceMovie:
             arr = arr.astype(np.float32)
         arr = np.ascontiguousarray(arr).reshape(len(ids), self.d)
         t = torch.from_numpy(arr)
-        self.h2d_bytes += t.numel() * t.element_size()
         return t.pin_memory() if torch.cuda.is_available() else t
 
-    def _host_batches(self):
-        for f0 in range(self.lo, self.hi, self.batch_frames):
-            f1 = min(self.hi, f0 + self.batch_frames)
-            yield f0, f1, self._host_frames(range(f0, f1))
+    def _stage(self, n):
+        """One of two reusable pinned staging buffers (its previous async copy is waited for first)."""
+        if self._staging is None:
+            self._staging = [[torch.empty((self.upload_frames, self.d), dtype=self.torch_dtype, pin_memory=True), None]
+                             for _ in range(2)]
+            self._stage_turn = 0
+        slot = self._staging[self._stage_turn]
+        self._stage_turn ^= 1
+        if slot[1] is not None:
+            slot[1].synchronize()
+        return slot, slot[0][:n]
+
+    def _upload(self, f0, f1, dst):
+        """Enqueue the host -> device copy of global frames [f0, f1) into dst on the copy stream; returns
+        the event that marks its completion."""
+        n = f1 - f0
+        with torch.cuda.stream(self._copy_stream):
+            if self._host2d is not None and self._pinned_src:
+                dst.copy_(self._host2d[f0:f1], non_blocking=True)
+                slot = None
+            else:
+                slot, buf = self._stage(n)
+                if self._host2d is not None:
+                    buf.copy_(self._host2d[f0:f1])
+                else:
+                    arr = np.asarray(self._src[list(range(f0, f1))])
+                    arr = arr[None] if arr.ndim == 2 else arr
+                    buf.copy_(torch.from_numpy(np.ascontiguousarray(arr).reshape(n, self.d)))
+                dst.copy_(buf, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self._copy_stream)
+            if slot is not None:
+                slot[1] = ev
+        self.h2d_bytes += n * self.d * dst.element_size()
+        return ev
+
+    def _fill(self):
+        for _ in self.batches():
+            pass
+        torch.cuda.current_stream(self.device).synchronize()
 
     def batches(self):
-        """Yield (first local frame index, (n, d) device tensor) covering the shard once."""
-        if self._resident is not None:
-            step = self.batch_frames * 8
+        """Yield (first local frame index, (n, d) device tensor) covering the shard once, in order."""
+        cur = torch.cuda.current_stream(self.device)
+        if self._resident is not None and self._filled:
+            step = max(self.batch_frames * 8, 65536)
             for s in range(0, self.n_local, step):
                 yield s, self._resident[s : s + step]
+        elif self._resident is not None:
+            # first pass: upload chunk by chunk, two copies in flight ahead of the consumer
+            self._copy_stream.wait_stream(cur)
+            spans = [(f0, min(self.hi, f0 + self.upload_frames)) for f0 in range(self.lo, self.hi, self.upload_frames)]
+            evs = {}
+            ahead = 2
+            for i in range(min(ahead, len(spans))):
+                evs[i] = self._upload(spans[i][0], spans[i][1], self._resident[spans[i][0] - self.lo : spans[i][1] - self.lo])
+            for i, (f0, f1) in enumerate(spans):
+                cur.wait_event(evs.pop(i))
+                yield f0 - self.lo, self._resident[f0 - self.lo : f1 - self.lo]
+                j = i + ahead
+                if j < len(spans):
+                    evs[j] = self._upload(spans[j][0], spans[j][1], self._resident[spans[j][0] - self.lo : spans[j][1] - self.lo])
+            self._filled = True
         else:
-            for f0, f1, chunk in self._host_batches():
-                yield f0 - self.lo, chunk.to(self.device, non_blocking=True)
+            self._copy_stream.wait_stream(cur)
+            for f0 in range(self.lo, self.hi, self.upload_frames):
+                f1 = min(self.hi, f0 + self.upload_frames)
+                chunk = torch.empty((f1 - f0, self.d), dtype=self.torch_dtype, device=self.device)
+                cur.wait_event(self._upload(f0, f1, chunk))
+                chunk.record_stream(cur)
+                yield f0 - self.lo, chunk
+
+    def frame_source(self, global_frame_ids):
+        """(2-D device tensor, int64 device row indices) addressing the requested frames without copying
+        them when the shard is resident; otherwise the frames are gathered first."""
+        ids = [int(i) for i in global_frame_ids]
+        if self._resident is not None and all(self.lo <= i < self.hi for i in ids):
+            if not self._filled:
+                self._fill()
+            return self._resident, torch.as_tensor(ids, dtype=torch.int64, device=self.device) - self.lo
+        g = self.gather(ids)
+        return g, torch.arange(g.shape[0], dtype=torch.int64, device=self.device)
 
     def gather(self, global_frame_ids):
         """(n, d) device tensor (native dtype) of arbitrary global frames (any shard)."""
         ids = [int(i) for i in global_frame_ids]
         if self._resident is not None and all(self.lo <= i < self.hi for i in ids):
+            if not self._filled:
+                self._fill()
             idx = torch.as_tensor(ids, dtype=torch.int64, device=self.device) - self.lo
             return _index_rows(self._resident, idx)
-        if isinstance(self._src, torch.Tensor):
+        if isinstance(self._src, torch.Tensor) and self._src.is_cuda:
             idx = torch.as_tensor(ids, dtype=torch.int64, device=self._src.device)
             return _index_rows(self._src.view(self.T_total, self.d), idx).to(self.device)
-        return self._host_frames(ids).to(self.device)
+        if self._host2d is not None:
+            idx = torch.as_tensor(ids, dtype=torch.int64)
+            host = _index_rows(self._host2d, idx)
+            self.h2d_bytes += host.numel() * host.element_size()
+            return host.to(self.device)
+        host = self._host_frames(ids)
+        self.h2d_bytes += host.numel() * host.element_size()
+        return host.to(self.device)

@@ -200,8 +200,10 @@ def background_basis(movie: DeviceMovie, mean, std, bg_frames, bg_sketch, backgr
 
 
 def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, chunk=50):
-    """decomposition.py:147-189: roughness statistics of the rank-1 rSVD of pure-noise blocks."""
+    """decomposition.py:147-189: roughness statistics of the rank-1 rSVD of pure-noise blocks.
+    Every simulated block is its own tiny pixel-major movie (b, ld) for the block kernels."""
     b = bh * bw
+    ld = (t_win + 3) // 4 * 4
     starts = torch.zeros((chunk, 2), dtype=torch.int32, device=device)
     sp, tp = [], []
     have_noise = getattr(draws, "sim_noise", None) is not None
@@ -209,29 +211,29 @@ def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, 
     n_iters = len(draws.sim_noise) if have_noise else iters
     for s0 in range(0, n_iters, chunk):
         m = min(chunk, n_iters - s0)
+        noise = torch.zeros((m, b, ld), dtype=torch.float32, device=device)
         if have_noise:
-            noise = torch.stack(
-                [_as_dev(np.asarray(draws.sim_noise[s0 + i]).transpose(2, 0, 1).reshape(t_win, b), device) for i in range(m)]
-            )
+            for i in range(m):
+                noise[i, :, :t_win] = _as_dev(np.asarray(draws.sim_noise[s0 + i]).reshape(b, t_win), device)
         else:
-            noise = torch.randn((m, t_win, b), generator=gen, device=device, dtype=torch.float32)
+            noise[:, :, :t_win] = torch.randn((m, b, t_win), generator=gen, device=device, dtype=torch.float32)
         if have_sk:
             sk = torch.stack([_as_dev(draws.sim_sketch[s0 + i], device) for i in range(m)])
         else:
             sk = torch.randn((m, t_win, 11), generator=gen, device=device, dtype=torch.float32)
         l = sk.shape[2]
-        y = torch.bmm(noise.transpose(1, 2), sk)  # (m, b, l)
+        y = torch.bmm(noise[:, :, :t_win], sk)  # (m, b, l)
         q = ops.orthonormalize_cols(y)  # (m, b, l)
         rp = (l + 3) // 4 * 4
         qp = torch.zeros((m, b, rp), dtype=torch.float32, device=device)
         qp[:, :, :l] = q
-        bq = ops.block_project(noise, t_win * b, t_win, bw, b, starts[:m], bh, bw, qp, l)  # (m, l, t)
+        bq = ops.block_project(noise, b * ld, ld, bw, starts[:m], bh, bw, qp, l)  # (m, l, ld)
         _, e = ops.jacobi_eigh(ops.gram_rows(bq), mode=0)
         e1 = e[:, :, :1].contiguous()  # (m, l, 1)
         u1 = torch.zeros((m, b, 4), dtype=torch.float32, device=device)
         u1[:, :, :1] = torch.bmm(q, e1)
-        v1 = torch.bmm(e1.transpose(1, 2), bq).contiguous()  # (m, 1, t) == s * v
-        ss, ts, _ = ops.block_stats_rank(u1, v1, bh, bw, 1, float("inf"), float("inf"), 1)
+        v1 = torch.bmm(e1.transpose(1, 2), bq).contiguous()  # (m, 1, ld) == s * v
+        ss, ts, _ = ops.block_stats_rank(u1, v1, bh, bw, 1, float("inf"), float("inf"), 1, t=t_win)
         sp.append(ss.reshape(-1))
         tp.append(ts.reshape(-1))
     sp = torch.cat(sp).cpu().numpy()
@@ -239,22 +241,23 @@ def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, 
     return np.percentile(sp.flatten(), sim_conf), np.percentile(tp.flatten(), sim_conf)
 
 
-def block_decompositions(yres, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_t, mcf, sketches):
+def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_t, mcf, sketches):
     """single_block_md (decomposition.py:235-330) for all blocks at once.
-    yres (t, d) float32, already cropped to a multiple of taf.  sketches (nb, t//taf, r+10).
-    Returns U (nb, b, rp), V (nb, r, t), ranks (nb,), sstat, tstat."""
-    dev = yres.device
-    t, d = yres.shape
+    yt (d, ld) float32: pixel-major standardised init movie, t frames (a multiple of taf), zero padded
+    to ld.  sketches (nb, t//taf, r+10).
+    Returns U (nb, b, rp), V (nb, r, ld), ranks (nb,), sstat, tstat."""
+    dev = yt.device
+    d, ld = yt.shape
     nb = starts_dev.shape[0]
     rp = (r + 3) // 4 * 4
-    bta = ops.block_pool_tavg(yres, d2, starts_dev, bh, bw, saf, taf)  # (nb, t', P) = B_ta^T
+    bta = ops.block_pool_tavg(yt, t, d2, starts_dev, bh, bw, saf, taf)  # (nb, P, t') = B_ta
     _submark("blocks.pool")
-    P = bta.shape[2]
+    P = bta.shape[1]
     l = sketches.shape[2]
     if P > l:
-        y = torch.bmm(bta.transpose(1, 2), sketches)  # (nb, P, l)
+        y = torch.bmm(bta, sketches)  # (nb, P, l)
         q = ops.orthonormalize_cols(y)
-        bq = torch.bmm(q.transpose(1, 2), bta.transpose(1, 2)).contiguous()  # (nb, l, t')
+        bq = torch.bmm(q.transpose(1, 2), bta).contiguous()  # (nb, l, t')
         _, e = ops.jacobi_eigh(ops.gram_rows(bq), mode=0)
         uds = torch.bmm(q, e[:, :, :r]).contiguous()  # (nb, P, r)
         del y, q, bq, e
@@ -262,29 +265,30 @@ def block_decompositions(yres, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_t
         # reduced QR of a P x l sketch with P <= l spans R^P: the rSVD is the exact SVD of B_ta
         if r > P:
             raise TypeError("max_components larger than the pooled block (jax.lax.dynamic_slice would fail)")
-        c = ops.gram_f64(bta, nb, P, bta.shape[1], bta.shape[1] * P, 1, P)
-        _, e = ops.jacobi_eigh(c, mode=0)
+        _, e = ops.jacobi_eigh(ops.gram_rows(bta), mode=0)
         uds = e[:, :, :r].contiguous()
     del bta
     _submark("blocks.rsvd")
     w4 = ops.block_unpool(uds, bh, bw, saf, rp)  # (nb, b, rp)
-    vds = ops.block_project(yres, 0, t, d2, d, starts_dev, bh, bw, w4, r)  # (nb, r, t)
+    vds = ops.block_project(yt, 0, ld, d2, starts_dev, bh, bw, w4, r)  # (nb, r, ld)
     del w4
     _submark("blocks.project1")
     g4 = ops.gram_rows(vds)
     _submark("blocks.gram1")
-    _, tm = ops.jacobi_eigh(g4, mode=1)  # E diag(1/sqrt(w))
+    _, tm = ops.jacobi_eigh(g4, mode=1)  # E diag(1/sqrt(w)): tm^T vds is the orthonormal temporal basis
     _submark("blocks.jacobi1")
-    vb = torch.bmm(tm.transpose(1, 2), vds)  # orthonormal temporal basis (nb, r, t)
+    # S = B (tm^T V_ds)^T = (B V_ds^T) tm : the r x t basis change is applied to the small b x r product
+    s_raw = ops.block_spatial(yt, 0, ld, d2, starts_dev, bh, bw, vds, rp)  # (nb, b, rp)
     del vds
-    _submark("blocks.bmm_vb")
-    s = ops.block_spatial(yres, 0, t, d2, d, starts_dev, bh, bw, vb, rp)  # (nb, b, rp)
-    del vb
     _submark("blocks.spatial")
+    tpad = torch.zeros((nb, rp, rp), dtype=torch.float32, device=dev)
+    tpad[:, :r, :r] = tm
+    s = torch.bmm(s_raw, tpad)
+    del s_raw
     uf = ops.orthonormalize_cols(s, r)  # (nb, b, rp)
     del s
     _submark("blocks.orth_s")
-    vn = ops.block_project(yres, 0, t, d2, d, starts_dev, bh, bw, uf, r)  # (nb, r, t)
+    vn = ops.block_project(yt, 0, ld, d2, starts_dev, bh, bw, uf, r)  # (nb, r, ld)
     _submark("blocks.project2")
     g6 = ops.gram_rows(vn)
     _submark("blocks.gram2")
@@ -293,10 +297,10 @@ def block_decompositions(yres, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_t
     lpad = torch.zeros((nb, rp, rp), dtype=torch.float32, device=dev)
     lpad[:, :r, :r] = lmat
     u = torch.bmm(uf, lpad)  # (nb, b, rp)
-    v = torch.bmm(lmat.transpose(1, 2), vn)  # (nb, r, t)
+    v = torch.bmm(lmat.transpose(1, 2), vn)  # (nb, r, ld)
     del uf, vn
     _submark("blocks.bmm_uv")
-    sstat, tstat, ranks = ops.block_stats_rank(u, v, bh, bw, r, thr_s, thr_t, mcf)
+    sstat, tstat, ranks = ops.block_stats_rank(u, v, bh, bw, r, thr_s, thr_t, mcf, t=t)
     _submark("blocks.stats")
     return u, v, ranks, sstat, tstat
 
@@ -317,9 +321,18 @@ class SparseU:
         self.tasks = torch.from_numpy(ops.make_tasks(ranks_host)).to(ranks_dev.device)
         self._csr = None
         self.supertiles = None
-        if len(ranks_host) and bh * bw <= 512:
-            rows = sorted(set(int(x) for x in starts[:, 0]))
-            cols = sorted(set(int(x) for x in starts[:, 1]))
+        self.strips = None
+        rows = sorted(set(int(x) for x in starts[:, 0])) if len(ranks_host) else []
+        cols = sorted(set(int(x) for x in starts[:, 1])) if len(ranks_host) else []
+        regular = len(ranks_host) > 0 and len(rows) * len(cols) == len(ranks_host) and np.array_equal(
+            np.asarray(starts, dtype=np.int64), np.array([(a, c) for a in rows for c in cols], dtype=np.int64))
+        if regular:
+            st = ops.make_strips(rows, cols, bh, bw, d1, d2, ranks_host, self.col0_host, bg.shape[0])
+            if st is not None:
+                dev = ranks_dev.device
+                self.strips = {k: (torch.from_numpy(v).to(dev) if k in ("items", "slot_ptr", "tasks") else v) for k, v in st.items()}
+                self.upack = ops.pack_strip_u(st, uvals32, bg, bh * bw)
+        if self.strips is None and len(ranks_host) and bh * bw <= 512:
             if len(rows) * len(cols) == len(ranks_host):
                 st = ops.make_supertiles(rows, cols, bh, bw, ranks_host, self.col0_host)
                 if st["max_h"] * st["max_w"] <= 2048:
@@ -361,20 +374,42 @@ class SparseU:
         indptr[1:] = torch.cumsum(counts, 0)
         return indptr, cols.to(torch.int32), vals
 
+    def gram(self):
+        """U^T U in float64 as (CSR of the local x local part, C = U^T bg^T (n_cols, K)): the two sparse products
+        of decomposition.py:974-981 reduce to applying these to the right factor."""
+        if getattr(self, "_gram", None) is None:
+            dev = self.uvals64.device
+            bg64 = self.bg.to(torch.float64).contiguous()
+            blk_of_col = torch.repeat_interleave(
+                torch.arange(len(self.ranks_host), device=dev, dtype=torch.int32), self.ranks_dev.to(torch.int64)).contiguous()
+            c = ops.project_cols_f64(bg64, self.d2, self.starts_dev, self.bh, self.bw, blk_of_col, self.col0_dev, self.uvals64,
+                                     bg64)  # (n_cols, K)
+            if self.n_local > 0:
+                csr = ops.utu_local_csr(self.starts, self.starts_dev, self.bh, self.bw, self.ranks_host, self.ranks_dev,
+                                        self.col0_host, self.col0_dev, self.uvals64)
+            else:
+                csr = None
+            self._gram = (csr, c)
+        return self._gram
+
     def utu_times_f64(self, right64):
-        """U^T U right in float64 (the two sparse products of decomposition.py:974-981)."""
-        if getattr(self, "_csr64", None) is None:
-            ip, ix, v = self.csr()
-            self._csr64 = (ip.contiguous(), ix.contiguous(), v.contiguous())
-            self._blk_of_col = torch.repeat_interleave(
-                torch.arange(len(self.ranks_host), device=v.device, dtype=torch.int32), self.ranks_dev.to(torch.int64)
-            ).contiguous()
-        ip, ix, v = self._csr64
-        d = self.d1 * self.d2
-        pix = torch.arange(d, dtype=torch.int32, device=right64.device)
-        w = ops.reconstruct_f64(ip, ix, v, right64.contiguous(), pix)  # (m, d): columns of U right as frames
-        return ops.project_cols_f64(w, self.d2, self.starts_dev, self.bh, self.bw, self._blk_of_col, self.col0_dev,
-                                    self.uvals64, self.bg.to(torch.float64).contiguous())
+        """U^T U right in float64 (right: (n_cols, m))."""
+        csr, c = self.gram()
+        nl = self.n_local
+        right64 = right64.contiguous()
+        z = torch.empty_like(right64)
+        r_bg = right64[nl:]
+        if nl > 0:
+            rowptr, cols, vals = csr
+            r_loc = right64[:nl].contiguous()
+            rows = torch.arange(nl, dtype=torch.int32, device=right64.device)
+            z[:nl] = ops.reconstruct_f64(rowptr, cols, vals, r_loc, rows).t()
+            z[:nl] += torch.matmul(c[:nl], r_bg)
+            z[nl:] = torch.matmul(c[:nl].t(), r_loc)
+        else:
+            z[nl:] = 0
+        z[nl:] += torch.matmul(c[nl:], r_bg)
+        return z
 
     def csr_physical32(self):
         if self._csr is None:
@@ -392,6 +427,10 @@ class SparseU:
     def project(self, movie2d, mean, inv_std, z):
         """z[:, :n] (R, ldz) (+)= U^T standardised(movie2d)   (K7a + K7b)."""
         n = movie2d.shape[0]
+        if self.strips is not None:
+            ops.project_stream(movie2d, self.d2, self.strips, self.upack, mean, inv_std, z[: self.n_local], z[self.n_local :])
+            _submark("project.stream")
+            return
         if self.n_local > 0:
             if self.supertiles is not None:
                 ops.project_supertile(movie2d, self.d2, self.supertiles, self.bh, self.bw, self.uvals32, mean, inv_std,
@@ -418,9 +457,12 @@ def compute_lowrank_factorized_svd(u, v, only_left=False):
     R = u.n_cols
     right = v.to(torch.float64) if R > v.shape[1] else torch.eye(R, dtype=torch.float64, device=dev)
     z = u.utu_times_f64(right)  # (R, m) float64
+    _submark("whiten.utu")
     g = torch.matmul(right.t(), z)
     g = 0.5 * (g + g.t())
+    _submark("whiten.gram")
     vals, vecs = sym_eigh_desc_abs(g)
+    _submark("whiten.eigh")
     # "eig_vals > 0" (decomposition.py:988) evaluated in float64: drop what is numerically zero
     good = vals > vals[0] * 1e-13
     vals, vecs = vals[good], vecs[:, good]
@@ -467,7 +509,9 @@ def projected_svd(projection, data, group=None):
         if group is not None:
             dist.all_reduce(gram, group=group)
         gram = 0.5 * (gram + gram.t())
+        _submark("final_svd.gram")
         vals, left = sym_eigh_desc_abs(gram)
+        _submark("final_svd.eigh")
         sing = torch.sqrt(vals).to(torch.float32)
         left = left.to(torch.float32)
         div = torch.where(sing == 0, torch.ones_like(sing), sing)
@@ -610,22 +654,9 @@ def localmd_decomposition(
         tm.mark("thresholds")
 
         # ---- init frames: standardise + background removal (pmd_loader.py:348-389) ----------------
-        raw = movie.gather(frames)
-        yres = ops.standardize_frames(raw, torch.arange(raw.shape[0], device=dev), mean, std)  # (t, d)
-        del raw
-        vbg = torch.matmul(bg, yres.t()).contiguous()  # (K, t)
-        yres.addmm_(vbg.t(), bg, alpha=-1.0)
-        if pixel_weighting is not None:
-            yres *= _as_dev(np.asarray(pixel_weighting, dtype=np.float32).reshape(-1), dev)[None, :]
-        t_init = yres.shape[0]
-        tm.mark("init_filter")
-
-        dim_1_iters, dim_2_iters = tile_starts(d1, bh), tile_starts(d2, bw)
-        starts = np.array([(k, j) for k in dim_1_iters for j in dim_2_iters], dtype=np.int32)
-        nb = starts.shape[0]
-        starts_dev = torch.from_numpy(starts).to(dev)
-        block_weights = pyramid_weights(bh, bw)
-
+        # Only the first crop = (t // taf) * taf init frames are ever used (decomposition.py:773-774); they
+        # are written straight into the pixel-major layout of the block kernels.
+        t_init = len(frames)
         if temporal_avg_factor >= t_init:
             raise ValueError("Need at least {} frames".format(temporal_avg_factor))
         if t_init // temporal_avg_factor <= max_components:
@@ -635,6 +666,22 @@ def localmd_decomposition(
         r = int(max_components)
         if r + 10 > 112:
             raise ValueError("max_components > 102 is not supported by the sm_100a Jacobi kernel")
+        if r > 64:
+            raise ValueError("max_components > 64 is not supported by the sm_100a block kernels")
+        src2d, idx = movie.frame_source(frames[:crop])
+        yt = ops.standardize_frames_t(src2d, idx, mean, std)  # (d, ld)
+        del src2d, idx
+        vbg = torch.matmul(bg, yt).contiguous()  # (K, ld)
+        yt.addmm_(bg.t(), vbg, alpha=-1.0)
+        if pixel_weighting is not None:
+            yt *= _as_dev(np.asarray(pixel_weighting, dtype=np.float32).reshape(-1), dev)[:, None]
+        tm.mark("init_filter")
+
+        dim_1_iters, dim_2_iters = tile_starts(d1, bh), tile_starts(d2, bw)
+        starts = np.array([(k, j) for k in dim_1_iters for j in dim_2_iters], dtype=np.int32)
+        nb = starts.shape[0]
+        starts_dev = torch.from_numpy(starts).to(dev)
+        block_weights = pyramid_weights(bh, bw)
 
         # ---- block fits (decomposition.py:790-838) -------------------------------------------------
         bs = take("block_sketches")
@@ -643,7 +690,7 @@ def localmd_decomposition(
         else:
             sketches = torch.randn((nb, crop // temporal_avg_factor, r + 10), generator=gen, device=dev, dtype=torch.float32)
         u_blk, v_blk, ranks_dev, sstat, tstat = block_decompositions(
-            yres[:crop], d2, starts_dev, bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
+            yt, crop, d2, starts_dev, bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
             int(max_consecutive_failures), sketches,
         )
         del sketches
@@ -657,8 +704,8 @@ def localmd_decomposition(
         su = _assemble(u_blk, starts, starts_dev, bh, bw, d1, d2, ranks_host, ranks_dev, block_weights, cumw, bg)
         blk_of_col = torch.repeat_interleave(torch.arange(nb, device=dev), ranks_dev.to(torch.int64))
         comp_of_col = torch.arange(su.n_local, device=dev) - su.col0_dev[blk_of_col]
-        v_init = torch.cat([v_blk[blk_of_col, comp_of_col], vbg[:, :crop]], dim=0)  # (R, t)
-        del u_blk, v_blk, yres
+        v_init = torch.cat([v_blk[blk_of_col, comp_of_col][:, :crop], vbg[:, :crop]], dim=0)  # (R, t)
+        del u_blk, v_blk, yt
         say("The total rank before pruning is {}".format(su.n_cols))
         if timings is not None:
             timings["__info__"] = dict(n_cols=int(su.n_cols), n_local=int(su.n_local), nb=int(nb), mean_rank=float(ranks_host.mean()),
@@ -702,6 +749,8 @@ def localmd_decomposition(
                                     vt.contiguous(), (T, d1, d2), order, mean, std, dev)
         tm.mark("export")
         tm.finish()
+        if timings is not None and "__info__" in timings:
+            timings["__info__"]["h2d_bytes"] = int(movie.h2d_bytes)
         _ACTIVE_TIMER = None
         if details is not None:
             details.update(

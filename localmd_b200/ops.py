@@ -158,13 +158,27 @@ def orthonormalize_cols(x, ncols=None, passes=2):
     return x
 
 
-def block_pool_tavg(yres, d2, starts, bh, bw, saf, taf):
-    _req(yres, torch.float32, "yres"), _req(starts, torch.int32, "starts")
-    t, d = yres.shape
+def standardize_frames_t(movie2d, frames, mean, stdv, ld=None):
+    """Pixel-major standardised init movie: out[p, i] = (movie[frames[i], p] - mean[p]) / std[p] as float32
+    (d, ld); ld defaults to len(frames) rounded up to a multiple of 4, padding columns are zero."""
+    _req(mean, torch.float32, "mean"), _req(stdv, torch.float32, "stdv"), _req(frames, torch.int64, "frames")
+    d = movie2d.shape[1]
+    n = frames.numel()
+    ld = (n + 3) // 4 * 4 if ld is None else int(ld)
+    out = torch.empty((d, ld), dtype=torch.float32, device=movie2d.device)
+    _call("pmd_standardize_frames_t", _p(movie2d), movie_dtype_code(movie2d), d, _p(frames), n, _p(mean), _p(stdv), _p(out), ld,
+          _stream())
+    return out
+
+
+def block_pool_tavg(yt, t, d2, starts, bh, bw, saf, taf):
+    """(nb, P, t // taf) pooled + time-averaged blocks of the pixel-major init movie yt (d, ld)."""
+    _req(yt, torch.float32, "yt"), _req(starts, torch.int32, "starts")
+    d, ld = yt.shape
     nb = starts.shape[0]
     ph, pw = -(-bh // saf), -(-bw // saf)
-    bta = torch.empty((nb, t // taf, ph * pw), dtype=torch.float32, device=yres.device)
-    _call("pmd_block_pool_tavg", _p(yres), t, d2, d, _p(starts), nb, bh, bw, saf, taf, _p(bta), _stream())
+    bta = torch.empty((nb, ph * pw, t // taf), dtype=torch.float32, device=yt.device)
+    _call("pmd_block_pool_tavg", _p(yt), ld, t, d2, _p(starts), nb, bh, bw, saf, taf, _p(bta), _stream())
     return bta
 
 
@@ -176,42 +190,47 @@ def block_unpool(uds, bh, bw, saf, rp):
     return w
 
 
-def block_project(movie, movie_batch_stride, t, d2, d, starts, bh, bw, w, r):
-    _req(movie, torch.float32, "movie"), _req(w, torch.float32, "w"), _req(starts, torch.int32, "starts")
+def block_project(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, w, r, ldo=None):
+    """out[b, c, f] = sum_q w[b, q, c] * Y_b[q, f] over the pixel-major movie (leading dimension ld).
+    Returns (nb, r, ldo) float32 (ldo defaults to ld; columns past the data are zero)."""
+    _req(movie_t, torch.float32, "movie_t"), _req(w, torch.float32, "w"), _req(starts, torch.int32, "starts")
     nb, bpix, rp = w.shape
     assert bpix == bh * bw and starts.shape[0] == nb
-    out = torch.empty((nb, r, t), dtype=torch.float32, device=movie.device)
+    ldo = ld if ldo is None else int(ldo)
+    out = torch.empty((nb, r, ldo), dtype=torch.float32, device=movie_t.device)
     step = 65535
     for s in range(0, nb, step):
         m = min(step, nb - s)
-        mv = ctypes.c_void_p(movie.data_ptr() + 4 * s * movie_batch_stride)
-        _call("pmd_block_project", mv, movie_batch_stride, t, d2, d, _p(starts[s:]), m, bh, bw, _p(w[s:]), r, rp,
-              _p(out[s:]), _stream())
+        mv = ctypes.c_void_p(movie_t.data_ptr() + 4 * s * movie_batch_stride)
+        _call("pmd_block_project", mv, movie_batch_stride, ld, d2, _p(starts[s:]), m, bh, bw, _p(w[s:]), r, rp, _p(out[s:]),
+              ldo, _stream())
     return out
 
 
-def block_spatial(movie, movie_batch_stride, t, d2, d, starts, bh, bw, vb, rp):
-    _req(movie, torch.float32, "movie"), _req(vb, torch.float32, "vb"), _req(starts, torch.int32, "starts")
-    nb, r, tt = vb.shape
-    assert tt == t
-    s_out = torch.empty((nb, bh * bw, rp), dtype=torch.float32, device=movie.device)
+def block_spatial(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, v, rp):
+    """s[b, q, c] = sum_f Y_b[q, f] * v[b, c, f];  v (nb, r, ldv) with zero padding -> (nb, bh*bw, rp)."""
+    _req(movie_t, torch.float32, "movie_t"), _req(v, torch.float32, "v"), _req(starts, torch.int32, "starts")
+    nb, r, ldv = v.shape
+    s_out = torch.empty((nb, bh * bw, rp), dtype=torch.float32, device=movie_t.device)
     step = 65535
     for s in range(0, nb, step):
         m = min(step, nb - s)
-        mv = ctypes.c_void_p(movie.data_ptr() + 4 * s * movie_batch_stride)
-        _call("pmd_block_spatial", mv, movie_batch_stride, t, d2, d, _p(starts[s:]), m, bh, bw, _p(vb[s:]), r, rp,
+        mv = ctypes.c_void_p(movie_t.data_ptr() + 4 * s * movie_batch_stride)
+        _call("pmd_block_spatial", mv, movie_batch_stride, ld, d2, _p(starts[s:]), m, bh, bw, _p(v[s:]), ldv, r, rp,
               _p(s_out[s:]), _stream())
     return s_out
 
 
-def block_stats_rank(u, v, bh, bw, r, thr_s, thr_t, max_fail):
+def block_stats_rank(u, v, bh, bw, r, thr_s, thr_t, max_fail, t=None):
+    """v: (nb, r, ldv); the temporal statistic uses the first t columns of every row (default: all)."""
     _req(u, torch.float32, "u"), _req(v, torch.float32, "v")
     nb, bpix, rp = u.shape
-    t = v.shape[2]
+    ldv = v.shape[2]
+    t = ldv if t is None else int(t)
     sstat = torch.empty((nb, r), dtype=torch.float32, device=u.device)
     tstat = torch.empty((nb, r), dtype=torch.float32, device=u.device)
     ranks = torch.empty((nb,), dtype=torch.int32, device=u.device)
-    _call("pmd_block_stats_rank", _p(u), _p(v), nb, bh, bw, r, rp, t, float(thr_s), float(thr_t), int(max_fail), _p(sstat),
+    _call("pmd_block_stats_rank", _p(u), _p(v), nb, bh, bw, r, rp, t, ldv, float(thr_s), float(thr_t), int(max_fail), _p(sstat),
           _p(tstat), _p(ranks), _stream())
     return sstat, tstat, ranks
 
@@ -293,6 +312,50 @@ def project_cols_f64(w64, d2, starts, bh, bw, blk_of_col, col0, uvals64, bg64):
     return z
 
 
+def overlap_pairs(starts, bh, bw):
+    """All ordered pairs (b1, b2) of blocks whose windows intersect, sorted by (b1, b2).  Host logic."""
+    starts = np.asarray(starts, dtype=np.int64).reshape(-1, 2)
+    nb = starts.shape[0]
+    rows, cols = np.unique(starts[:, 0]), np.unique(starts[:, 1])
+    if len(rows) * len(cols) == nb and np.array_equal(
+            starts, np.stack(np.meshgrid(rows, cols, indexing="ij"), axis=-1).reshape(-1, 2)):
+        ar, ar2 = np.nonzero(np.abs(rows[:, None] - rows[None, :]) < bh)
+        ac, ac2 = np.nonzero(np.abs(cols[:, None] - cols[None, :]) < bw)
+        nbc = len(cols)
+        b1 = (ar[:, None] * nbc + ac[None, :]).reshape(-1)
+        b2 = (ar2[:, None] * nbc + ac2[None, :]).reshape(-1)
+    else:  # arbitrary block lists
+        hit = (np.abs(starts[:, None, 0] - starts[None, :, 0]) < bh) & (np.abs(starts[:, None, 1] - starts[None, :, 1]) < bw)
+        b1, b2 = np.nonzero(hit)
+    order = np.lexsort((b2, b1))
+    return np.stack([b1[order], b2[order]], axis=1).astype(np.int32)
+
+
+def utu_local_csr(starts_host, starts, bh, bw, ranks_host, ranks, col0_host, col0, uvals64):
+    """Canonical CSR (rowptr int64, cols int32, vals float64) of U_loc^T U_loc on the device."""
+    _req(uvals64, torch.float64, "uvals64"), _req(ranks, torch.int32, "ranks"), _req(col0, torch.int64, "col0")
+    dev = uvals64.device
+    ranks_host = np.asarray(ranks_host, dtype=np.int64)
+    pairs = overlap_pairs(starts_host, bh, bw)
+    b1, b2 = pairs[:, 0].astype(np.int64), pairs[:, 1].astype(np.int64)
+    r2 = ranks_host[b2]
+    ex = np.cumsum(r2) - r2                                  # exclusive prefix of tile widths over all pairs
+    first = np.searchsorted(b1, np.arange(len(ranks_host)))  # first pair of every block (pairs sorted by b1)
+    rowoff = ex - ex[first[b1]]
+    row_width = np.bincount(b1, weights=r2, minlength=len(ranks_host)).astype(np.int64)
+    rowptr = np.concatenate([[0], np.cumsum(np.repeat(row_width, ranks_host))]).astype(np.int64)
+    nnz = int(rowptr[-1])
+    vals = torch.empty(nnz, dtype=torch.float64, device=dev)
+    cols = torch.empty(nnz, dtype=torch.int32, device=dev)
+    rowptr_d = torch.from_numpy(rowptr).to(dev)
+    if nnz:
+        pairs_d = torch.from_numpy(pairs).to(dev)  # named: the tensors must outlive the pointer extraction
+        rowoff_d = torch.from_numpy(rowoff.astype(np.int64)).to(dev)
+        _call("pmd_utu_pairs", _p(pairs_d), pairs.shape[0], _p(rowoff_d), _p(starts), bh, bw, _p(ranks), _p(col0), _p(uvals64),
+              _p(rowptr_d), _p(vals), _p(cols), _stream())
+    return rowptr_d, cols, vals
+
+
 def split_groups(rk):
     """Split `rk` kept components into ceil(rk/4) groups of nearly equal size (each <= 4)."""
     ng = (rk + 3) // 4
@@ -348,3 +411,189 @@ def project_supertile(movie2d, d2, st, bh, bw, uvals32, mean, inv_std, z):
     _call("pmd_project_supertile", _p(movie2d), movie_dtype_code(movie2d), t, d2, d, _p(st["tiles"]), st["tiles"].shape[0],
           _p(st["task_ptr"]), _p(st["tasks"]), bh, bw, st["max_h"], st["max_w"], _p(uvals32), _p(mean), _p(inv_std), _p(z),
           z.stride(0), _stream())
+
+
+# ---------------------------------------------------------------------------------------------
+# K7 v3: host tables of pmd_project_stream
+# ---------------------------------------------------------------------------------------------
+PS_WARPS, PS_MAX_RW = 8, 48
+
+
+def _split8(rk):
+    """Split rk kept components into tasks of <= 8 components (sizes as equal as possible)."""
+    n = (rk + 7) // 8
+    base, extra = divmod(rk, n)
+    return [base + (1 if i < extra else 0) for i in range(n)]
+
+
+def _pack_slots(tasks, n_slots):
+    """Greedy interval packing of tasks (sorted by first row) into ONE pass of n_slots task lists whose row ranges are
+    disjoint and ascending.  Returns (slots, leftovers)."""
+    slots = [[] for _ in range(n_slots)]
+    left = []
+    for tk in tasks:
+        for s in slots:
+            if not s or s[-1][0] + s[-1][2] <= tk[0]:
+                s.append(tk)
+                break
+        else:
+            left.append(tk)
+    return slots, left
+
+
+def _pack_passes(tasks, n_slots):
+    """All passes needed for `tasks`: the first takes what fits; leftovers are clustered by contiguous row coverage so
+    that every extra pass only streams the rows its tasks need.  Returns [(row0, row1, slots), ...]."""
+    out = []
+    slots, left = _pack_slots(tasks, n_slots)
+    used = [tk for s in slots for tk in s]
+    if used:
+        out.append((min(tk[0] for tk in used), max(tk[0] + tk[2] for tk in used), slots))
+    while left:
+        cluster, end, rest = [], None, []
+        for tk in left:
+            if end is None or tk[0] < end:
+                cluster.append(tk)
+                end = tk[0] + tk[2] if end is None else max(end, tk[0] + tk[2])
+            else:
+                rest.append(tk)
+        slots, more = _pack_slots(cluster, n_slots)
+        used = [tk for s in slots for tk in s]
+        out.append((min(tk[0] for tk in used), max(tk[0] + tk[2] for tk in used), slots))
+        left = sorted(more + rest, key=lambda x: x[0])
+    return out
+
+
+def make_strips(row_starts, col_starts, bh, bw, d1, d2, ranks_host, col0_host, n_bg, G=None):
+    """Host tables for pmd_project_stream (see include/pmd_sm100.h).  Blocks form the grid row_starts x col_starts
+    (numbered row-major).  Returns a dict with int32 arrays items [n,8], slot_ptr, tasks [m,12], the order in which
+    local tasks must be packed (`local8`, `local4`: arrays of (first column, n comps)), the background groups,
+    `n_parts` and `max_rw`; or None when a single block column is already wider than the kernel's strip limit."""
+    row_starts, col_starts = [int(x) for x in row_starts], [int(x) for x in col_starts]
+    nbr, nbc = len(row_starts), len(col_starts)
+    ranks = np.asarray(ranks_host, dtype=np.int64).reshape(nbr, nbc)
+    col0 = np.asarray(col0_host, dtype=np.int64).reshape(nbr, nbc)
+    if bw > PS_MAX_RW:
+        return None
+    bpix = bh * bw
+    bg_groups = [(k0, min(8, n_bg - k0)) for k0 in range(0, n_bg, 8)]
+
+    def build(g):
+        local8, local4, items = [], [], []
+        total_rw = 0
+        for part, ca in enumerate(range(0, nbc, g)):
+            cb = min(ca + g, nbc)
+            c0, c1 = col_starts[ca], col_starts[cb - 1] + bw
+            if c1 - c0 > PS_MAX_RW:
+                return None
+            core_end = col_starts[cb] if cb < nbc else d2
+            tasks = []
+            # background tasks first (they keep their slot for the whole strip); (by, bx, h, w, col, nc, ncp, kind, key)
+            for gi, (k0, nc) in enumerate(bg_groups):
+                tasks.append((0, 0, d1, core_end - c0, k0, nc, 8 if nc > 4 else 4, 1, gi))
+            loc = []
+            for a in range(nbr):
+                for c in range(ca, cb):
+                    first = int(col0[a, c])
+                    for nc in _split8(int(ranks[a, c])):
+                        loc.append((row_starts[a], col_starts[c] - c0, bh, bw, first, nc, 8 if nc > 4 else 4, 0, None))
+                        first += nc
+            loc.sort(key=lambda x: x[0])
+            for (row0, row1, slots) in _pack_passes(tasks + loc, PS_WARPS):
+                items.append(dict(c0=c0, rw=c1 - c0, slots=slots, bg_part=part, row0=row0, n_rows=row1 - row0))
+                total_rw += (c1 - c0) * (row1 - row0)
+        return items, total_rw
+
+    best = None
+    for g in ([G] if G else range(1, 9)):
+        res = build(g)
+        if res is None:
+            break
+        if best is None or res[1] < best[1]:
+            best = res
+    if best is None:
+        return None
+    items, _ = best
+    n8 = n4 = 0
+    for itm in items:
+        for s in itm["slots"]:
+            for tk in s:
+                if tk[7] == 0:
+                    if tk[6] == 8:
+                        n8 += 1
+                    else:
+                        n4 += 1
+    base4 = n8 * bpix * 8
+    base_bg = base4 + n4 * bpix * 4
+    bg_off, off = [], base_bg
+    for (k0, nc) in bg_groups:
+        ncp = 8 if nc > 4 else 4
+        bg_off.append(off)
+        off += d1 * d2 * ncp
+    local8, local4 = [], []
+    it_arr, slot_ptr, task_arr = [], [], []
+    for itm in items:
+        it_arr.append((itm["c0"], itm["rw"], len(slot_ptr), itm["n_rows"], itm["bg_part"], itm["row0"], 0, 0))
+        for s in itm["slots"]:
+            slot_ptr.append(len(task_arr))
+            for (by, bx, h, w, col, nc, ncp, kind, key) in s:
+                if kind == 0:
+                    if ncp == 8:
+                        uoff = len(local8) * bpix * 8
+                        local8.append((col, nc))
+                    else:
+                        uoff = base4 + len(local4) * bpix * 4
+                        local4.append((col, nc))
+                    urow = bw * ncp
+                else:
+                    uoff = bg_off[key] + itm["c0"] * ncp
+                    urow = d2 * ncp
+                task_arr.append((by, bx, h, w, col, nc, ncp, urow, uoff & 0xFFFFFFFF, uoff >> 32, kind, 0))
+        slot_ptr.append(len(task_arr))
+    u32 = lambda a, w: np.array(a, dtype=np.int64).astype(np.uint32).view(np.int32).reshape(-1, w)  # noqa: E731
+    return dict(items=np.array(it_arr, dtype=np.int32).reshape(-1, 8), slot_ptr=np.array(slot_ptr, dtype=np.int32),
+                tasks=u32(task_arr, 12), local8=np.array(local8, dtype=np.int64).reshape(-1, 2),
+                local4=np.array(local4, dtype=np.int64).reshape(-1, 2), bg_groups=bg_groups, upack_floats=off,
+                n_parts=1 + max(i["bg_part"] for i in items),
+                max_rw=max(i["rw"] for i in items), n_items=len(items))
+
+
+def pack_strip_u(st, uvals32, bg, bpix):
+    """upack for pmd_project_stream: per local task [pixel][padded comps], then per background group [pixel][comps]."""
+    dev = uvals32.device
+    n_local = uvals32.shape[0]
+    upack = torch.zeros(st["upack_floats"], dtype=torch.float32, device=dev)
+    uvp = torch.cat([uvals32, torch.zeros((1, bpix), dtype=torch.float32, device=dev)], dim=0)  # row n_local = zeros
+    pos = 0
+    for key, ncp in (("local8", 8), ("local4", 4)):
+        lt = st[key]
+        if len(lt):
+            idx = lt[:, :1] + np.arange(ncp)[None, :]
+            idx = np.where(np.arange(ncp)[None, :] < lt[:, 1:2], idx, n_local)
+            g = uvp[torch.from_numpy(idx).to(dev)]  # (ntask, ncp, bpix)
+            n = g.numel()
+            upack[pos : pos + n] = g.permute(0, 2, 1).reshape(-1)
+            pos += n
+    K, d = bg.shape
+    for (k0, nc) in st["bg_groups"]:
+        ncp = 8 if nc > 4 else 4
+        blk = torch.zeros((d, ncp), dtype=torch.float32, device=dev)
+        blk[:, :nc] = bg[k0 : k0 + nc].t()
+        upack[pos : pos + d * ncp] = blk.reshape(-1)
+        pos += d * ncp
+    assert pos == st["upack_floats"]
+    return upack
+
+
+def project_stream(movie2d, d2, st_dev, upack, mean, inv_std, z_local, z_bg):
+    """One streaming pass: z_local[col, f] (local columns) and z_bg[k, f] (dense background columns) of
+    U^T standardised movie.  st_dev: make_strips() tables with items/slot_ptr/tasks as device tensors."""
+    t, d = movie2d.shape
+    assert z_local.dtype == torch.float32 and (z_local.numel() == 0 or z_local.stride(1) == 1)
+    K = z_bg.shape[0]
+    parts = torch.empty((st_dev["n_parts"], K, t), dtype=torch.float32, device=movie2d.device)
+    zl = z_local if z_local.numel() else parts
+    _call("pmd_project_stream", _p(movie2d), movie_dtype_code(movie2d), t, d2, d, _p(st_dev["items"]), st_dev["n_items"],
+          _p(st_dev["slot_ptr"]), _p(st_dev["tasks"]), st_dev["max_rw"], _p(upack), _p(mean), _p(inv_std), _p(zl),
+          zl.stride(0) if z_local.numel() else t, _p(parts), t, K * t, _stream())
+    z_bg[:, :t].copy_(parts.sum(dim=0))

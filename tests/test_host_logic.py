@@ -159,3 +159,47 @@ def test_lazy_data_loader_contract():
         a[0:11]
     with pytest.raises(IndexError):
         a["x"]
+
+
+def test_overlap_pairs_host():
+    from localmd_b200 import ops as host_ops
+
+    starts = np.array([(k, j) for k in O.tile_starts(52, 20) for j in O.tile_starts(33, 20)], dtype=np.int32)
+    pairs = host_ops.overlap_pairs(starts, 20, 20)
+    hit = (np.abs(starts[:, None, 0] - starts[None, :, 0]) < 20) & (np.abs(starts[:, None, 1] - starts[None, :, 1]) < 20)
+    b1, b2 = np.nonzero(hit)
+    assert np.array_equal(pairs, np.stack([b1, b2], axis=1))
+    shuffled = starts[::-1].copy()
+    pairs2 = host_ops.overlap_pairs(shuffled, 20, 20)  # arbitrary order -> generic path
+    hit2 = (np.abs(shuffled[:, None, 0] - shuffled[None, :, 0]) < 20) & (np.abs(shuffled[:, None, 1] - shuffled[None, :, 1]) < 20)
+    assert np.array_equal(pairs2, np.stack(np.nonzero(hit2), axis=1))
+
+
+def test_strip_tables():
+    """make_strips: every (block, component) and every (pixel, background component) is owned by exactly one task;
+    the tasks of one warp slot never overlap in rows; extra passes only stream the rows they need."""
+    from localmd_b200 import ops as host_ops
+
+    rng = np.random.default_rng(5)
+    for (d1, d2, bh, bw, n_bg, hi) in [(112, 95, 20, 20, 15, 14), (61, 83, 10, 10, 1, 4), (70, 96, 32, 32, 9, 30), (40, 40, 40, 40, 3, 5)]:
+        rs, cs = O.tile_starts(d1, bh), O.tile_starts(d2, bw)
+        ranks = rng.integers(1, hi + 1, len(rs) * len(cs))
+        col0 = np.concatenate([[0], np.cumsum(ranks)[:-1]])
+        st = host_ops.make_strips(rs, cs, bh, bw, d1, d2, ranks, col0, n_bg)
+        items, slot_ptr, tasks = st["items"], st["slot_ptr"], st["tasks"]
+        assert st["max_rw"] <= host_ops.PS_MAX_RW
+        seen_cols = np.zeros(int(ranks.sum()), int)
+        bg_cover = np.zeros((n_bg, d1, d2), int)
+        for (c0, rw, sp, n_rows, part, row0, _, _) in items:
+            for w in range(host_ops.PS_WARPS):
+                end = -1
+                for ti in range(slot_ptr[sp + w], slot_ptr[sp + w + 1]):
+                    by, bx, h, wd, col, nc, ncp, urow, ulo, uhi, kind, _ = tasks[ti]
+                    assert by >= end and by >= row0 and by + h <= row0 + n_rows and bx + wd <= rw and 1 <= nc <= ncp <= 8
+                    end = by + h
+                    if kind == 0:
+                        seen_cols[col : col + nc] += 1
+                        assert (h, wd) == (bh, bw) and urow == bw * ncp
+                    else:
+                        bg_cover[col : col + nc, by : by + h, c0 + bx : c0 + bx + wd] += 1
+        assert np.all(seen_cols == 1) and np.all(bg_cover == 1)

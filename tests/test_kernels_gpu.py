@@ -107,12 +107,35 @@ def _block_setup(rng, t, d1, d2, bh, bw):
     return y, starts
 
 
+def _pixel_major(y, ld=None):
+    """(t, d1, d2) -> pixel-major (d, ld) float32 with zero padding columns."""
+    t = y.shape[0]
+    ld = (t + 3) // 4 * 4 if ld is None else ld
+    yt = np.zeros((y.shape[1] * y.shape[2], ld), np.float32)
+    yt[:, :t] = y.reshape(t, -1).T
+    return yt
+
+
+def test_standardize_frames_t(ops):
+    rng = np.random.default_rng(3)
+    T, d = 77, 1000
+    movie = rng.integers(0, 4000, size=(T, d)).astype(np.uint16)
+    mean = rng.uniform(1000, 3000, d).astype(np.float32)
+    std = rng.uniform(0.5, 40, d).astype(np.float32)
+    frames = rng.choice(T, 41, replace=False).astype(np.int64)
+    out = ops.standardize_frames_t(dev(movie), dev(frames), dev(mean), dev(std)).cpu().numpy()
+    assert out.shape == (d, 44)
+    ref = ((movie[frames].astype(np.float32) - mean) / std).T
+    np.testing.assert_array_equal(out[:, :41], ref)  # same float32 operations as the reference: bit exact
+    assert np.all(out[:, 41:] == 0)
+
+
 @pytest.mark.parametrize("bh,bw,saf,taf", [(16, 16, 2, 10), (10, 14, 2, 5), (11, 13, 2, 4), (12, 12, 3, 6), (20, 20, 2, 10)])
 def test_block_pool_tavg_and_unpool(ops, bh, bw, saf, taf):
     rng = np.random.default_rng(bh * bw)
     t, d1, d2 = 120, 33, 41
     y, starts = _block_setup(rng, t, d1, d2, bh, bw)
-    bta = ops.block_pool_tavg(dev(y).view(t, -1), d2, dev(starts), bh, bw, saf, taf).cpu().numpy()
+    bta = ops.block_pool_tavg(dev(_pixel_major(y)), t, d2, dev(starts), bh, bw, saf, taf).cpu().numpy()
     r = 3
     ph, pw = -(-bh // saf), -(-bw // saf)
     uds = rng.standard_normal((len(starts), ph * pw, r)).astype(np.float32)
@@ -121,14 +144,15 @@ def test_block_pool_tavg_and_unpool(ops, bh, bw, saf, taf):
         block = y[:, i0 : i0 + bh, j0 : j0 + bw].transpose(1, 2, 0)
         ds = O.downsample_average_pooling(block, saf)
         ta = ds.reshape(ph * pw, t // taf, taf).mean(axis=2)  # C-order pooled pixel index, consecutive frame bins
-        np.testing.assert_allclose(bta[b].T, ta, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(bta[b], ta, rtol=1e-5, atol=1e-6)
         lhs = w4[b][:, :r].T.astype(np.float64) @ block.reshape(bh * bw, t).astype(np.float64)
         rhs = uds[b].T.astype(np.float64) @ ds.reshape(ph * pw, t).astype(np.float64)
         np.testing.assert_allclose(lhs, rhs, atol=1e-4)
         assert np.all(w4[b][:, r:] == 0)
 
 
-@pytest.mark.parametrize("bh,bw,r,t", [(16, 16, 8, 300), (20, 20, 50, 130), (10, 12, 5, 64), (40, 40, 13, 100)])
+@pytest.mark.parametrize("bh,bw,r,t", [(16, 16, 8, 300), (20, 20, 50, 130), (10, 12, 5, 64), (40, 40, 13, 100), (22, 22, 64, 515),
+                                       (32, 32, 50, 259), (10, 10, 1, 30)])
 def test_block_project_and_spatial(ops, bh, bw, r, t):
     rng = np.random.default_rng(r + t)
     d1, d2 = 47, 52
@@ -137,29 +161,36 @@ def test_block_project_and_spatial(ops, bh, bw, r, t):
     rp = (r + 3) // 4 * 4
     w = np.zeros((nb, bh * bw, rp), np.float32)
     w[:, :, :r] = rng.standard_normal((nb, bh * bw, r))
-    yd, sd = dev(y).view(t, -1), dev(starts)
-    out = ops.block_project(yd, 0, t, d2, d1 * d2, sd, bh, bw, dev(w), r).cpu().numpy()
-    vb = rng.standard_normal((nb, r, t)).astype(np.float32)
-    s = ops.block_spatial(yd, 0, t, d2, d1 * d2, sd, bh, bw, dev(vb), rp).cpu().numpy()
+    yt = _pixel_major(y)
+    ld = yt.shape[1]
+    yd, sd = dev(yt), dev(starts)
+    out = ops.block_project(yd, 0, ld, d2, sd, bh, bw, dev(w), r).cpu().numpy()
+    assert out.shape == (nb, r, ld)
+    vb = np.zeros((nb, r, ld), np.float32)
+    vb[:, :, :t] = rng.standard_normal((nb, r, t))
+    s = ops.block_spatial(yd, 0, ld, d2, sd, bh, bw, dev(vb), rp).cpu().numpy()
     for b, (i0, j0) in enumerate(starts):
         blk = y[:, i0 : i0 + bh, j0 : j0 + bw].reshape(t, bh * bw).T.astype(np.float64)  # (b, t)
         ref = w[b][:, :r].T.astype(np.float64) @ blk
-        np.testing.assert_allclose(out[b], ref, rtol=1e-4, atol=2e-5 * np.abs(ref).max())
-        ref_s = blk @ vb[b].T.astype(np.float64)
+        np.testing.assert_allclose(out[b][:, :t], ref, rtol=1e-4, atol=2e-5 * np.abs(ref).max())
+        assert np.all(out[b][:, t:] == 0)
+        ref_s = blk @ vb[b][:, :t].T.astype(np.float64)
         np.testing.assert_allclose(s[b][:, :r], ref_s, rtol=1e-4, atol=2e-5 * np.abs(ref_s).max())
         assert np.all(s[b][:, r:] == 0)
 
 
 def test_block_project_batched_movies(ops):
-    """movie_batch_stride != 0: every 'block' is its own small movie (threshold simulation)."""
+    """movie_batch_stride != 0: every 'block' is its own small pixel-major movie (threshold simulation)."""
     rng = np.random.default_rng(0)
     m, t, bh, bw, r = 5, 90, 12, 10, 3
-    movies = rng.standard_normal((m, t, bh * bw)).astype(np.float32)
+    ld = 92
+    movies = np.zeros((m, bh * bw, ld), np.float32)
+    movies[:, :, :t] = rng.standard_normal((m, bh * bw, t))
     w = np.zeros((m, bh * bw, 4), np.float32)
     w[:, :, :r] = rng.standard_normal((m, bh * bw, r))
     starts = np.zeros((m, 2), np.int32)
-    out = ops.block_project(dev(movies), t * bh * bw, t, bw, bh * bw, dev(starts), bh, bw, dev(w), r).cpu().numpy()
-    ref = np.einsum("mqc,mtq->mct", w[:, :, :r].astype(np.float64), movies.astype(np.float64))
+    out = ops.block_project(dev(movies), bh * bw * ld, ld, bw, dev(starts), bh, bw, dev(w), r).cpu().numpy()
+    ref = np.einsum("mqc,mqt->mct", w[:, :, :r].astype(np.float64), movies.astype(np.float64))
     np.testing.assert_allclose(out, ref, rtol=1e-4, atol=1e-4)
 
 
@@ -180,7 +211,8 @@ def test_block_stats_rank(ops, mcf):
             v[b, c] = tr
     v[3, 4] = 0.0  # NaN statistic -> failure
     thr_s, thr_t = 0.9, 1.5
-    ss, ts, ranks = ops.block_stats_rank(dev(u), dev(v), bh, bw, r, thr_s, thr_t, mcf)
+    vpad = np.concatenate([v, rng.standard_normal((nb, r, 3)).astype(np.float32)], axis=2)  # padding must be ignored
+    ss, ts, ranks = ops.block_stats_rank(dev(u), dev(vpad), bh, bw, r, thr_s, thr_t, mcf, t=t)
     ss, ts, ranks = ss.cpu().numpy(), ts.cpu().numpy(), ranks.cpu().numpy()
     for b in range(nb):
         u3 = u[b][:, :r].reshape(bh, bw, r)
@@ -291,6 +323,61 @@ def test_project_supertile(ops, bh, bw, max_rank, dtype, d1, d2):
     if dtype == np.float32:
         ops.project_supertile(dev(movie), d2, std_, bh, bw, dev(uv), None, None, z2)
         ref2 = (U.T @ movie.astype(np.float64).T)[:n_local]
+        np.testing.assert_allclose(z2.cpu().numpy(), ref2, rtol=0, atol=2e-5 * np.abs(ref2).max())
+
+
+@pytest.mark.parametrize("bh,bw,d1,d2,max_rank", [(20, 20, 112, 95, 5), (10, 14, 33, 47, 3), (16, 16, 16, 16, 4), (12, 12, 50, 37, 7)])
+def test_utu_gram_times(ops, bh, bw, d1, d2, max_rank):
+    """Block-sparse U^T U (pmd_utu_pairs + pmd_project_cols_f64) applied to a dense right factor."""
+    from localmd_b200.decomposition import SparseU
+
+    rng = np.random.default_rng(bh + d1)
+    K = 3
+    starts, ranks, col0, uv, bg, U = _random_sparse_u(rng, d1, d2, bh, bw, max_rank, K)
+    uv64 = uv.astype(np.float64)
+    su = SparseU(starts, dev(starts), bh, bw, d1, d2, ranks.astype(np.int64), dev(ranks), dev(uv64), dev(uv), dev(bg))
+    right = rng.standard_normal((U.shape[1], 9))
+    got = su.utu_times_f64(dev(right)).cpu().numpy()
+    ref = (U.T @ U) @ right
+    np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max())
+    rowptr, cols, vals = su.gram()[0]
+    n_local = int(ranks.sum())
+    L = sp.csr_matrix((vals.cpu().numpy(), cols.cpu().numpy(), rowptr.cpu().numpy()), shape=(n_local, n_local))
+    assert L.has_canonical_format
+    np.testing.assert_allclose(L.toarray(), (U.T @ U).toarray()[:n_local, :n_local], rtol=1e-11, atol=1e-12)
+
+
+@pytest.mark.parametrize(
+    "bh,bw,max_rank,dtype,d1,d2,K,T",
+    [(10, 10, 3, np.float32, 61, 83, 1, 300), (16, 16, 9, np.uint16, 61, 83, 5, 1100), (20, 20, 13, np.float32, 112, 95, 15, 777),
+     (22, 22, 20, np.int16, 61, 83, 9, 258), (20, 12, 6, np.float32, 64, 40, 16, 513), (20, 20, 2, np.float64, 20, 20, 2, 64),
+     (32, 32, 6, np.uint8, 70, 96, 3, 260), (40, 40, 11, np.float32, 90, 101, 4, 255)],
+)
+def test_project_stream(ops, bh, bw, max_rank, dtype, d1, d2, K, T):
+    """K7 v3 (strip-streaming kernel): local + dense columns in one pass, against float64 U^T Y."""
+    rng = np.random.default_rng(bh * 3 + max_rank)
+    starts, ranks, col0, uv, bg, U = _random_sparse_u(rng, d1, d2, bh, bw, max_rank, K)
+    y = rng.uniform(0, 200, size=(T, d1 * d2))
+    movie = (np.rint(y) if np.issubdtype(dtype, np.integer) else y).astype(dtype)
+    mean = rng.uniform(80, 120, d1 * d2).astype(np.float32)
+    std = rng.uniform(0.5, 2, d1 * d2).astype(np.float32)
+    inv = (1.0 / std).astype(np.float32)
+    n_local = int(ranks.sum())
+    st = ops.make_strips(O.tile_starts(d1, bh), O.tile_starts(d2, bw), bh, bw, d1, d2, ranks, col0, K)
+    assert st is not None
+    std_ = {k: (dev(v) if k in ("items", "slot_ptr", "tasks") else v) for k, v in st.items()}
+    upack = ops.pack_strip_u(st, dev(uv), dev(bg), bh * bw)
+    z = torch.full((n_local + K, T + 5), 7.0, dtype=torch.float32, device="cuda")
+    ops.project_stream(dev(movie), d2, std_, upack, dev(mean), dev(inv), z[:n_local], z[n_local:])
+    yc = (movie.astype(np.float32).astype(np.float64) - mean) / std
+    ref = U.T @ yc.T
+    got = z.cpu().numpy()
+    np.testing.assert_allclose(got[:, :T], ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+    assert np.all(got[:, T:] == 7.0)  # nothing written beyond the movie
+    if dtype == np.float32:
+        z2 = torch.zeros((n_local + K, T), dtype=torch.float32, device="cuda")
+        ops.project_stream(dev(movie), d2, std_, upack, None, None, z2[:n_local], z2[n_local:])
+        ref2 = U.T @ movie.astype(np.float64).T
         np.testing.assert_allclose(z2.cpu().numpy(), ref2, rtol=0, atol=2e-5 * np.abs(ref2).max())
 
 

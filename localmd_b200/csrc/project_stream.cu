@@ -25,8 +25,8 @@ constexpr int kPSWarps = 8;
 constexpr int kPSThreads = kPSWarps * 32;
 constexpr int kPSF = 256;          // frames per CTA
 constexpr int kPSMaxRW = 48;       // widest strip (pixels)
-constexpr int kPSPhases = 3;       // a row is staged / consumed in this many interleaved phases
-constexpr int kPSUnits = 4;        // staging units (pixel x 4 frames) per thread and phase
+constexpr int kPSPhases = 4;       // a row is staged / consumed in this many interleaved phases
+constexpr int kPSUnits = 2;        // staging units (pixel x 4 frames) per thread, pixel set and phase
 
 struct PSItem {                    // one CTA column: 8 ints
     int c0, rw, task_ptr, n_rows, bg_part, row0, pad1, pad2;
@@ -35,104 +35,160 @@ struct PSTask {                    // 12 ints
     int by, bx, h, w, col, nc, ncp, urow, uoff_lo, uoff_hi, kind, pad;
 };
 
-template <typename T>
+__device__ __forceinline__ void ps_cp_async16(void* smem, const void* gmem) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(a), "l"(gmem));
+}
+
+// SETS = ceil(strip width / 32): lane l stages pixels l (+32); warp w stages the 4-frame chunks w, w+8, ...
+// FULL: every frame of the tile exists (the host launches the last, partial tile separately with FULL = false).
+template <typename T, int SETS, bool FULL>
 __global__ void __launch_bounds__(kPSThreads, 2)
-project_stream_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_t d, const PSItem* __restrict__ items,
+project_stream_kernel(const T* __restrict__ movie, int64_t t, int64_t tile0, int64_t d2, int64_t d, const PSItem* __restrict__ items,
                       const int32_t* __restrict__ slot_ptr, const PSTask* __restrict__ tasks, const float* __restrict__ upack,
                       const float* __restrict__ mean, const float* __restrict__ inv_std, float* __restrict__ z, int64_t ldz,
                       float* __restrict__ zbg, int64_t ldzbg, int64_t bg_stride) {
     extern __shared__ __align__(16) float sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PSItem it = items[blockIdx.x];
-    const int rw = it.rw, c0 = it.c0, row_end = it.row0 + it.n_rows;
-    const int64_t f0 = (int64_t)blockIdx.y * kPSF;
-    float* xbuf[2] = {sm, sm + rw * kPSF};
-    float* ubuf = sm + 2 * rw * kPSF + warp * (kPSMaxRW * 8);
+    const int rw = it.rw, c0 = it.c0, row0 = it.row0, row_end = it.row0 + it.n_rows;
+    const int64_t f0 = (tile0 + blockIdx.y) * kPSF;
+    const int xstride = rw * kPSF;
+    float* const ubuf = sm + 2 * xstride + warp * (2 * kPSMaxRW * 8);   // two U slabs per warp
 
-    // ---- staging helpers --------------------------------------------------------------------------
-    const int nunits = rw * (kPSF / 4);
-    T pre[kPSUnits][4];
-    auto prefetch = [&](int row, int ph) {   // raw loads only: nothing here waits for them
+    // ---- staging -------------------------------------------------------------------------------------
+    // unit (s, m): pixel k = lane + 32 s, frames f0 + 4 c4 .. +3 with c4 = warp + 8 m (m = 0..7); phase ph handles
+    // m = 2 ph, 2 ph + 1.  Frames past the end of the movie are CLAMPED to the last frame: their results are never
+    // stored, so no predicate or zero fill is needed on the data path.
+    T pre[SETS][kPSUnits][4];
+    const T* const col_ptr = movie + c0 + lane;            // + row * d2 + frame * d
+    const int64_t fbase = f0 + 4 * warp;                   // first frame of unit m = 0
+    const int64_t ustep = 32 * d;                          // frames advance by 32 from unit to unit
+    int dst_off[SETS];
 #pragma unroll
-        for (int n = 0; n < kPSUnits; ++n) {
-            const int idx = tid + kPSThreads * (ph * kPSUnits + n);
-            if (idx < nunits) {
-                const int c4 = idx / rw, k = idx - c4 * rw;
-                const T* src = movie + (f0 + 4 * c4) * d + (int64_t)row * d2 + c0 + k;
+    for (int s = 0; s < SETS; ++s) {
+        const int k = lane + 32 * s;
+        dst_off[s] = k * kPSF + ((warp ^ (k & 7)) << 2);   // + 32 m  (c4 ^ (k & 7) = (warp ^ (k & 7)) + 8 m)
+    }
+    auto prefetch = [&](const T* rowp, int ph) {            // raw loads only: nothing here waits for them
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int64_t f = f0 + 4 * c4 + j;
-                    pre[n][j] = f < t ? src[(int64_t)j * d] : T(0);
+        for (int s = 0; s < SETS; ++s) {
+            if (lane + 32 * s < rw) {
+#pragma unroll
+                for (int n = 0; n < kPSUnits; ++n) {
+                    const int m = kPSUnits * ph + n;
+                    if (FULL) {
+                        const T* src = rowp + 32 * s + fbase * d + (int64_t)m * ustep;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) pre[s][n][j] = src[(int64_t)j * d];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const int64_t f = min(fbase + 32 * m + j, t - 1);
+                            pre[s][n][j] = rowp[32 * s + f * d];
+                        }
+                    }
                 }
             }
         }
     };
-    auto commit = [&](float* dst, int row, int ph) {   // centre, scale, transpose into x[pixel][frame]
+    float mu[SETS], is[SETS];
+    auto load_norm = [&](int row) {
 #pragma unroll
-        for (int n = 0; n < kPSUnits; ++n) {
-            const int idx = tid + kPSThreads * (ph * kPSUnits + n);
-            if (idx < nunits) {
-                const int c4 = idx / rw, k = idx - c4 * rw;
-                const int64_t pix = (int64_t)row * d2 + c0 + k;
-                const float mu = mean ? __ldg(mean + pix) : 0.f;
-                const float is = inv_std ? __ldg(inv_std + pix) : 1.f;
-                float v[4];
+        for (int s = 0; s < SETS; ++s) {
+            mu[s] = 0.f;
+            is[s] = 1.f;
+            if (lane + 32 * s < rw) {
+                const int64_t pix = (int64_t)row * d2 + c0 + lane + 32 * s;
+                if (mean) mu[s] = __ldg(mean + pix);
+                if (inv_std) is[s] = __ldg(inv_std + pix);
+            }
+        }
+    };
+    auto commit = [&](float* dst, int ph) {                 // centre, scale, transpose into x[pixel][frame]
 #pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = (f0 + 4 * c4 + j < t) ? (to_f32(pre[n][j]) - mu) * is : 0.f;
-                *reinterpret_cast<float4*>(dst + k * kPSF + ((c4 ^ (k & 7)) << 2)) = make_float4(v[0], v[1], v[2], v[3]);
+        for (int s = 0; s < SETS; ++s) {
+            if (lane + 32 * s < rw) {
+#pragma unroll
+                for (int n = 0; n < kPSUnits; ++n) {
+                    const int m = kPSUnits * ph + n;
+                    float4 v;
+                    v.x = (to_f32(pre[s][n][0]) - mu[s]) * is[s];
+                    v.y = (to_f32(pre[s][n][1]) - mu[s]) * is[s];
+                    v.z = (to_f32(pre[s][n][2]) - mu[s]) * is[s];
+                    v.w = (to_f32(pre[s][n][3]) - mu[s]) * is[s];
+                    *reinterpret_cast<float4*>(dst + dst_off[s] + 32 * m) = v;
+                }
             }
         }
     };
 
-    // ---- task state of this warp --------------------------------------------------------------------
+    // ---- task state of this warp ---------------------------------------------------------------------
     const int sp = it.task_ptr + warp;   // slot_ptr entries of this item: [task_ptr .. task_ptr + kPSWarps]
-    int tnext = slot_ptr[sp], tend = slot_ptr[sp + 1];
+    int tnext = slot_ptr[sp];
+    const int tend = slot_ptr[sp + 1];
     PSTask tk;
     tk.by = 1 << 30;
     tk.h = 0;
     if (tnext < tend) tk = tasks[tnext];
+    // U slab of task row r: [w][ncp] floats, contiguous in upack; fetched one row ahead with cp.async
+    auto fetch_slab = [&](int uoff_lo, int uoff_hi, int urow, int n4, int r, int buf) {
+        const int64_t uo = ((int64_t)uoff_hi << 32 | (uint32_t)uoff_lo) + (int64_t)r * urow;
+        const float4* usrc = reinterpret_cast<const float4*>(upack + uo);
+        float4* udst = reinterpret_cast<float4*>(ubuf + buf * (kPSMaxRW * 8));
+        for (int i = lane; i < n4; i += 32) ps_cp_async16(udst + i, usrc + i);
+    };
+    int ub = 0;                                            // slab buffer holding the current row of the current task
+    if (tk.by == row0) fetch_slab(tk.uoff_lo, tk.uoff_hi, tk.urow, (tk.w * tk.ncp) >> 2, 0, 0);
+    asm volatile("cp.async.commit_group;\n" ::);
+
     float acc[8][8];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
+    const T* rowp = col_ptr + (int64_t)row0 * d2;
+    load_norm(row0);
 #pragma unroll
     for (int ph = 0; ph < kPSPhases; ++ph) {
-        prefetch(it.row0, ph);
-        commit(xbuf[0], it.row0, ph);
+        prefetch(rowp, ph);
+        commit(sm, ph);
     }
     __syncthreads();
 
-    for (int row = it.row0; row < row_end; ++row) {
-        const float* xs = xbuf[(row - it.row0) & 1];
-        float* xn = xbuf[(row - it.row0 + 1) & 1];
+    for (int row = row0; row < row_end; ++row) {
+        const float* xs = sm + ((row - row0) & 1) * xstride;
+        float* xn = sm + ((row - row0 + 1) & 1) * xstride;
         const bool more = row + 1 < row_end;
+        rowp += d2;
+        if (more) load_norm(row + 1);
         const bool active = row >= tk.by && row < tk.by + tk.h;
-        const int w = tk.w, bx = tk.bx;
-        if (active) {
-            // U slab of this row: [w][ncp] floats, contiguous in upack
-            const int64_t uo = ((int64_t)tk.uoff_hi << 32 | (uint32_t)tk.uoff_lo) + (int64_t)(row - tk.by) * tk.urow;
-            const float4* usrc = reinterpret_cast<const float4*>(upack + uo);
-            const int n4 = (w * tk.ncp) >> 2;
-            for (int i = lane; i < n4; i += 32) reinterpret_cast<float4*>(ubuf)[i] = usrc[i];
-            __syncwarp();
+        const int w = tk.w;
+        const float* us = ubuf + ub * (kPSMaxRW * 8);
+        // the slab of this row was requested one row ago (or before the loop); request the next one
+        asm volatile("cp.async.wait_group 0;\n" ::);
+        __syncwarp();
+        if (active && row + 1 < tk.by + tk.h) {
+            fetch_slab(tk.uoff_lo, tk.uoff_hi, tk.urow, (w * tk.ncp) >> 2, row + 1 - tk.by, ub ^ 1);
+        } else if (!active && row + 1 == tk.by) {
+            fetch_slab(tk.uoff_lo, tk.uoff_hi, tk.urow, (w * tk.ncp) >> 2, 0, ub);   // starts next row: buffer is free
         }
+        asm volatile("cp.async.commit_group;\n" ::);
 #pragma unroll
         for (int ph = 0; ph < kPSPhases; ++ph) {
-            if (more) prefetch(row + 1, ph);
+            if (more) prefetch(rowp, ph);
             if (active) {
                 const int j0 = (w * ph) / kPSPhases, j1 = (w * (ph + 1)) / kPSPhases;
+                const float* xr = xs + (tk.bx + j0) * kPSF;
                 if (tk.ncp == 8) {
 #pragma unroll 1
-                    for (int j = j0; j < j1; ++j) {
-                        const int k = bx + j;
-                        const float* xr = xs + k * kPSF;
-                        const int sw = (lane ^ (k & 7)) << 2;
+                    for (int j = j0; j < j1; ++j, xr += kPSF) {
+                        const int sw = (lane ^ ((tk.bx + j) & 7)) << 2;
                         const float4 xa = *reinterpret_cast<const float4*>(xr + sw);
                         const float4 xb = *reinterpret_cast<const float4*>(xr + 128 + sw);
-                        const float4 u0 = *reinterpret_cast<const float4*>(ubuf + j * 8);
-                        const float4 u1 = *reinterpret_cast<const float4*>(ubuf + j * 8 + 4);
+                        const float4 u0 = *reinterpret_cast<const float4*>(us + j * 8);
+                        const float4 u1 = *reinterpret_cast<const float4*>(us + j * 8 + 4);
                         const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
                         const float uv[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
@@ -142,13 +198,11 @@ project_stream_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_
                     }
                 } else {
 #pragma unroll 1
-                    for (int j = j0; j < j1; ++j) {
-                        const int k = bx + j;
-                        const float* xr = xs + k * kPSF;
-                        const int sw = (lane ^ (k & 7)) << 2;
+                    for (int j = j0; j < j1; ++j, xr += kPSF) {
+                        const int sw = (lane ^ ((tk.bx + j) & 7)) << 2;
                         const float4 xa = *reinterpret_cast<const float4*>(xr + sw);
                         const float4 xb = *reinterpret_cast<const float4*>(xr + 128 + sw);
-                        const float4 u0 = *reinterpret_cast<const float4*>(ubuf + j * 4);
+                        const float4 u0 = *reinterpret_cast<const float4*>(us + j * 4);
                         const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
                         const float uv[4] = {u0.x, u0.y, u0.z, u0.w};
 #pragma unroll
@@ -158,8 +212,9 @@ project_stream_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_
                     }
                 }
             }
-            if (more) commit(xn, row + 1, ph);
+            if (more) commit(xn, ph);
         }
+        if (active) ub ^= 1;
         if (active && row == tk.by + tk.h - 1) {
             // the block (or the strip, for a background task) ends here: store and take the next task
             float* zo;
@@ -197,6 +252,10 @@ project_stream_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_
             ++tnext;
             if (tnext < tend) {
                 tk = tasks[tnext];
+                if (tk.by == row + 1) {                      // back-to-back tasks: the slab request above was skipped
+                    fetch_slab(tk.uoff_lo, tk.uoff_hi, tk.urow, (tk.w * tk.ncp) >> 2, 0, ub);
+                    asm volatile("cp.async.commit_group;\n" ::);
+                }
             } else {
                 tk.by = 1 << 30;
                 tk.h = 0;
@@ -204,6 +263,7 @@ project_stream_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_
         }
         __syncthreads();
     }
+    asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
 }  // namespace pmd
@@ -219,15 +279,27 @@ extern "C" int pmd_project_stream(const void* movie, int dtype, int64_t t, int64
     PMD_REQUIRE(((uintptr_t)upack & 15) == 0, fn, "upack must be 16-byte aligned");
     const int64_t ftiles = (t + pmd::kPSF - 1) / pmd::kPSF;
     PMD_REQUIRE(ftiles <= 65535, fn, "too many frames per call");
-    const size_t smem = (size_t)(2 * max_rw * pmd::kPSF + pmd::kPSWarps * pmd::kPSMaxRW * 8) * sizeof(float);
-    dim3 grid((unsigned)n_items, (unsigned)ftiles);
+    const size_t smem = (size_t)(2 * max_rw * pmd::kPSF + pmd::kPSWarps * 2 * pmd::kPSMaxRW * 8) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t full_tiles = t / pmd::kPSF;
+#define PMD_LAUNCH_PS(SETS, FULL, TILE0, NT)                                                                             \
+    if ((NT) > 0) {                                                                                                      \
+        auto k = pmd::project_stream_kernel<scalar_t, SETS, FULL>;                                                       \
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+        if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }         \
+        k<<<dim3((unsigned)n_items, (unsigned)(NT)), pmd::kPSThreads, smem, st>>>(                                       \
+            (const scalar_t*)movie, t, (int64_t)(TILE0), d2, d, (const pmd::PSItem*)items, slot_ptr,                     \
+            (const pmd::PSTask*)tasks, upack, mean, inv_std, z, ldz, zbg, ldzbg, bg_stride);                             \
+    }
     PMD_DISPATCH_DTYPE(dtype, fn, {
-        auto k = pmd::project_stream_kernel<scalar_t>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
-        k<<<grid, pmd::kPSThreads, smem, st>>>((const scalar_t*)movie, t, d2, d, (const pmd::PSItem*)items, slot_ptr,
-                                               (const pmd::PSTask*)tasks, upack, mean, inv_std, z, ldz, zbg, ldzbg, bg_stride);
+        if (max_rw <= 32) {
+            PMD_LAUNCH_PS(1, true, 0, full_tiles)
+            PMD_LAUNCH_PS(1, false, full_tiles, ftiles - full_tiles)
+        } else {
+            PMD_LAUNCH_PS(2, true, 0, full_tiles)
+            PMD_LAUNCH_PS(2, false, full_tiles, ftiles - full_tiles)
+        }
     });
+#undef PMD_LAUNCH_PS
     return pmd::check_launch(fn);
 }

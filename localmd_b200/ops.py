@@ -441,6 +441,21 @@ def _pack_slots(tasks, n_slots):
     return slots, left
 
 
+def _balance_slots(slots):
+    """Permute warp slots so that the work (rows x width x padded comps) is spread evenly over the four SM
+    sub-partitions (warp w issues on sub-partition w % 4)."""
+    n = len(slots)
+    load = [sum(tk[2] * tk[3] * tk[6] for tk in s) for s in slots]
+    order = sorted(range(n), key=lambda i: -load[i])
+    bucket_load, bucket_free = [0] * 4, [[b + 4 * j for j in range(n // 4)] for b in range(4)]
+    out = [None] * n
+    for i in order:
+        b = min((b for b in range(4) if bucket_free[b]), key=lambda b: bucket_load[b])
+        out[bucket_free[b].pop(0)] = slots[i]
+        bucket_load[b] += load[i]
+    return out
+
+
 def _pack_passes(tasks, n_slots):
     """All passes needed for `tasks`: the first takes what fits; leftovers are clustered by contiguous row coverage so
     that every extra pass only streams the rows its tasks need.  Returns [(row0, row1, slots), ...]."""
@@ -448,7 +463,7 @@ def _pack_passes(tasks, n_slots):
     slots, left = _pack_slots(tasks, n_slots)
     used = [tk for s in slots for tk in s]
     if used:
-        out.append((min(tk[0] for tk in used), max(tk[0] + tk[2] for tk in used), slots))
+        out.append((min(tk[0] for tk in used), max(tk[0] + tk[2] for tk in used), _balance_slots(slots)))
     while left:
         cluster, end, rest = [], None, []
         for tk in left:

@@ -53,6 +53,12 @@ def timeit(name, fn):
     print("%-18s %8.3f ms  %7.1f GB/s of movie bytes  (x%.1f to T=20000: %.1f ms)" % (name, ms, nbytes / ms / 1e6, 20000 / T, ms * 20000 / T))
 
 
+if which in ("all", "stream"):
+    sst = ops.make_strips(rows, cols, bh, bw, d1, d2, ranks, col0, K)
+    sst_d = {k: (torch.from_numpy(v).to(dev) if k in ("items", "slot_ptr", "tasks") else v) for k, v in sst.items()}
+    upack = ops.pack_strip_u(sst, uv, bg, bh * bw)
+    print("strips: items", sst["n_items"], "max_rw", sst["max_rw"], "tasks", len(sst["tasks"]))
+    timeit("project_stream", lambda: ops.project_stream(movie, d2, sst_d, upack, mean, inv, z[:n_local], z[n_local:]))
 if which in ("all", "supertile"):
     timeit("project_supertile", lambda: ops.project_supertile(movie, d2, std, bh, bw, uv, mean, inv, z[:n_local]))
 if which in ("all", "local"):

@@ -79,6 +79,15 @@ int pmd_jacobi_eigh(double* c, int64_t batch, int64_t n, int mode, double* w, fl
 int pmd_standardize_frames_t(const void* movie, int dtype, int64_t d, const int64_t* frames, int64_t n_frames,
                              const float* mean, const float* stdv, float* out, int64_t ld, void* stream);
 
+/* batched in-place orthonormalisation of the first n columns of x [batch][m][ldx] (float32), one CTA per matrix held
+ * in shared memory (n <= 64):  if g_ext != NULL first  X <- X L_g^-T  with g_ext[b] = L_g L_g^T ([batch][n][n]
+ * float64: used with the Gram of the temporal components so that X = block * V^T becomes block * (orthonormal
+ * temporal basis)^T, decomposition.py:301-306); then `passes` rounds of CholQR (float64 Gram, in-kernel Cholesky,
+ * triangular solve).  Numerically dependent columns are set to zero.
+ * replaces: jnp.linalg.qr at decomposition.py:64 and the basis-producing SVDs at 301 and 315. */
+int pmd_block_orth(float* x, int64_t batch, int64_t m, int64_t n, int64_t ldx, const double* g_ext,
+                   int64_t passes, void* stream);
+
 /* 2x2(-ish) average pooling + temporal averaging of every block of the standardised init movie.
  * replaces: decomposition.py:192-232 (downsample_average_pooling) + 283-290.
  * yt: pixel-major init movie [d][ld] float32 (frame f of pixel p at yt[p*ld+f]), t frames used.

@@ -223,7 +223,7 @@ def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, 
             sk = torch.randn((m, t_win, 11), generator=gen, device=device, dtype=torch.float32)
         l = sk.shape[2]
         y = torch.bmm(noise[:, :, :t_win], sk)  # (m, b, l)
-        q = ops.orthonormalize_cols(y)  # (m, b, l)
+        q = ops.block_orth(y) if ops.block_orth_fits(b, l) else ops.orthonormalize_cols(y)  # (m, b, l)
         rp = (l + 3) // 4 * 4
         qp = torch.zeros((m, b, rp), dtype=torch.float32, device=device)
         qp[:, :, :l] = q
@@ -256,7 +256,7 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
     l = sketches.shape[2]
     if P > l:
         y = torch.bmm(bta, sketches)  # (nb, P, l)
-        q = ops.orthonormalize_cols(y)
+        q = ops.block_orth(y) if ops.block_orth_fits(P, l) else ops.orthonormalize_cols(y)
         bq = torch.bmm(q.transpose(1, 2), bta).contiguous()  # (nb, l, t')
         _, e = ops.jacobi_eigh(ops.gram_rows(bq), mode=0)
         uds = torch.bmm(q, e[:, :, :r]).contiguous()  # (nb, P, r)
@@ -273,20 +273,22 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
     vds = ops.block_project(yt, 0, ld, d2, starts_dev, bh, bw, w4, r)  # (nb, r, ld)
     del w4
     _submark("blocks.project1")
-    g4 = ops.gram_rows(vds)
+    g4 = ops.gram_rows(vds)  # (nb, r, r) float64: V_ds V_ds^T
     _submark("blocks.gram1")
-    _, tm = ops.jacobi_eigh(g4, mode=1)  # E diag(1/sqrt(w)): tm^T vds is the orthonormal temporal basis
-    _submark("blocks.jacobi1")
-    # S = B (tm^T V_ds)^T = (B V_ds^T) tm : the r x t basis change is applied to the small b x r product
+    # S = B Vb^T with Vb = L^-1 V_ds an orthonormal basis of the row space of V_ds (G = L L^T), i.e.
+    # S = (B V_ds^T) L^-T: the r x t basis change is applied to the small b x r product inside pmd_block_orth,
+    # which then orthonormalises S (decomposition.py:301-315; only the spans matter downstream).
     s_raw = ops.block_spatial(yt, 0, ld, d2, starts_dev, bh, bw, vds, rp)  # (nb, b, rp)
     del vds
     _submark("blocks.spatial")
-    tpad = torch.zeros((nb, rp, rp), dtype=torch.float32, device=dev)
-    tpad[:, :r, :r] = tm
-    s = torch.bmm(s_raw, tpad)
+    if ops.block_orth_fits(bh * bw, r):
+        uf = ops.block_orth(s_raw, r, g_ext=g4)  # (nb, b, rp)
+    else:  # large blocks: eigen-whitening of the temporal basis + Gram/Jacobi orthonormalisation in global memory
+        _, tm = ops.jacobi_eigh(g4, mode=1)
+        tpad = torch.zeros((nb, rp, rp), dtype=torch.float32, device=dev)
+        tpad[:, :r, :r] = tm
+        uf = ops.orthonormalize_cols(torch.bmm(s_raw, tpad), r)
     del s_raw
-    uf = ops.orthonormalize_cols(s, r)  # (nb, b, rp)
-    del s
     _submark("blocks.orth_s")
     vn = ops.block_project(yt, 0, ld, d2, starts_dev, bh, bw, uf, r)  # (nb, r, ld)
     _submark("blocks.project2")
@@ -446,10 +448,15 @@ class SparseU:
         ops.project_dense(movie2d, self.bg, mean, inv_std, zb)
 
 
-def compute_lowrank_factorized_svd(u, v, only_left=False):
+def compute_lowrank_factorized_svd(u, v, only_left=False, factor="eigh"):
     """decomposition.py:936-1010 on the GPU.  `u` is a SparseU (or a scipy sparse matrix, converted),
     `v` a dense (R, t') tensor/array.  Returns the spatial mixing matrix P (R, k) (device tensor) such
-    that U P has orthonormal columns; with only_left=False also (s, Vt) of the factorised product."""
+    that U P has orthonormal columns; with only_left=False also (s, Vt) of the factorised product.
+
+    factor="eigh" reproduces the reference's P = M E diag(1/sqrt(lambda)) (columns ordered by eigenvalue).
+    factor="chol" (used by localmd_decomposition, whose next step re-diagonalises anyway) takes P = M L^-T
+    from the float64 Cholesky factor G = L L^T: the same column space, hence the same final (R, s, Vt) in exact
+    arithmetic, without the t' x t' eigenproblem; it falls back to "eigh" when G is numerically singular."""
     if not isinstance(u, SparseU):
         u = sparse_u_from_scipy(u)
     dev = u.uvals32.device
@@ -461,12 +468,21 @@ def compute_lowrank_factorized_svd(u, v, only_left=False):
     g = torch.matmul(right.t(), z)
     g = 0.5 * (g + g.t())
     _submark("whiten.gram")
-    vals, vecs = sym_eigh_desc_abs(g)
-    _submark("whiten.eigh")
-    # "eig_vals > 0" (decomposition.py:988) evaluated in float64: drop what is numerically zero
-    good = vals > vals[0] * 1e-13
-    vals, vecs = vals[good], vecs[:, good]
-    mix64 = torch.matmul(right, vecs) / torch.sqrt(vals)[None, :]
+    mix64 = None
+    if factor == "chol" and only_left:
+        chol, info = torch.linalg.cholesky_ex(g)
+        dg = torch.diagonal(chol)
+        ok = (info == 0) & (dg.min() > 1e-6 * dg.max())  # cond(G) < ~1e12 : safe in float64
+        if bool(ok.item()):
+            mix64 = torch.linalg.solve_triangular(chol, right.t(), upper=False).t()
+            _submark("whiten.chol")
+    if mix64 is None:
+        vals, vecs = sym_eigh_desc_abs(g)
+        _submark("whiten.eigh")
+        # "eig_vals > 0" (decomposition.py:988) evaluated in float64: drop what is numerically zero
+        good = vals > vals[0] * 1e-13
+        vals, vecs = vals[good], vecs[:, good]
+        mix64 = torch.matmul(right, vecs) / torch.sqrt(vals)[None, :]
     mix = mix64.to(torch.float32)
     if only_left:
         return mix
@@ -725,9 +741,9 @@ def localmd_decomposition(
                     raise ValueError("prune_sketch has shape %s, expected %s" % (tuple(ps.shape), shape))
             else:
                 ps = torch.randn(shape, generator=gen, device=dev, dtype=torch.float32)
-            p = compute_lowrank_factorized_svd(su, torch.matmul(v_init, ps), only_left=True)
+            p = compute_lowrank_factorized_svd(su, torch.matmul(v_init, ps), only_left=True, factor="chol")
         else:
-            p = compute_lowrank_factorized_svd(su, v_init, only_left=True)
+            p = compute_lowrank_factorized_svd(su, v_init, only_left=True, factor="chol")
         say("After performing rank reduction, the updated rank is {}".format(p.shape[1]))
         tm.mark("whiten")
 

@@ -171,6 +171,24 @@ def standardize_frames_t(movie2d, frames, mean, stdv, ld=None):
     return out
 
 
+def block_orth_fits(m, n):
+    """True when an (m, n) matrix (+ its float64 Gram) fits the shared memory of pmd_block_orth."""
+    return n <= 64 and (n * (n | 1) + 2 * n) * 8 + m * (n | 1) * 4 <= 227 * 1024
+
+
+def block_orth(x, ncols=None, g_ext=None, passes=2):
+    """In-place fused orthonormalisation (pmd_block_orth) of the first ncols columns of every (m, ld) matrix of
+    x (batch, m, ld); optional float64 Gram g_ext (batch, ncols, ncols) for the pre-whitening solve.  Returns x."""
+    _req(x, torch.float32, "x")
+    b, m, ld = x.shape
+    n = ld if ncols is None else int(ncols)
+    if g_ext is not None:
+        _req(g_ext, torch.float64, "g_ext")
+        assert tuple(g_ext.shape) == (b, n, n)
+    _call("pmd_block_orth", _p(x), b, m, n, ld, _p(g_ext), passes, _stream())
+    return x
+
+
 def block_pool_tavg(yt, t, d2, starts, bh, bw, saf, taf):
     """(nb, P, t // taf) pooled + time-averaged blocks of the pixel-major init movie yt (d, ld)."""
     _req(yt, torch.float32, "yt"), _req(starts, torch.int32, "starts")

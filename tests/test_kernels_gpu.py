@@ -100,6 +100,50 @@ def test_orthonormalize_rank_deficient(ops):
         assert np.abs(proj - a[b]).max() < 1e-4  # span contains the original columns
 
 
+@pytest.mark.parametrize("m,n,ld,rank", [(100, 60, 60, 60), (400, 50, 52, 50), (400, 50, 52, 17), (144, 11, 11, 11), (30, 8, 12, 5)])
+def test_block_orth(ops, m, n, ld, rank):
+    """Fused CholQR2: orthonormal columns spanning the input's column space; dependent columns dropped."""
+    rng = np.random.default_rng(m + n)
+    nbat = 5
+    base = rng.standard_normal((nbat, m, rank)) * np.logspace(0, -3, rank)[None, None, :]
+    mix = rng.standard_normal((nbat, rank, n))
+    x = np.zeros((nbat, m, ld), np.float32)
+    x[:, :, :n] = base @ mix
+    x[:, :, n:] = 3.0  # padding columns must be left alone
+    q = ops.block_orth(dev(x.copy()), n).cpu().numpy()
+    for b in range(nbat):
+        qq = q[b][:, :n].astype(np.float64)
+        live = np.linalg.norm(qq, axis=0) > 0.5
+        # numerically dependent columns are dropped; float32 rounding of the input can keep a few of them alive
+        assert rank <= live.sum() <= n and (rank == n or live.sum() < n)
+        g = qq[:, live].T @ qq[:, live]
+        np.testing.assert_allclose(g, np.eye(int(live.sum())), atol=5e-6)
+        assert np.all(qq[:, ~live] == 0)
+        # same column space: projecting the input on span(Q) reproduces it
+        xin = x[b][:, :n].astype(np.float64)
+        proj = qq[:, live] @ (qq[:, live].T @ xin)
+        assert np.abs(proj - xin).max() < 2e-5 * np.abs(xin).max()
+        assert np.all(q[b][:, n:] == 3.0)
+
+
+def test_block_orth_with_external_gram(ops):
+    """X = B V^T with G = V V^T given: the result spans B * rowspace(V)^T and is orthonormal."""
+    rng = np.random.default_rng(4)
+    nbat, m, r, t = 3, 120, 12, 300
+    bmat = rng.standard_normal((nbat, m, t))
+    v = rng.standard_normal((nbat, r, t)) * np.logspace(0, -4, r)[None, :, None]
+    g = v @ v.transpose(0, 2, 1)
+    x = np.zeros((nbat, m, 12), np.float32)
+    x[:, :, :r] = bmat @ v.transpose(0, 2, 1)
+    q = ops.block_orth(dev(x.copy()), r, g_ext=dev(g)).cpu().numpy().astype(np.float64)
+    for b in range(nbat):
+        np.testing.assert_allclose(q[b].T @ q[b], np.eye(r), atol=5e-6)
+        vb = np.linalg.qr(v[b].T)[0]  # orthonormal basis of the row space
+        ref = bmat[b] @ vb
+        proj = q[b] @ (q[b].T @ ref)
+        assert np.abs(proj - ref).max() < 1e-3 * np.abs(ref).max()
+
+
 # ------------------------------------------------------------------------------------ block kernels
 def _block_setup(rng, t, d1, d2, bh, bw):
     y = rng.standard_normal((t, d1, d2)).astype(np.float32)

@@ -41,11 +41,11 @@ int pmd_abi_version(void);
  * this buffer (n_chunks = ceil(t_local/1024)).  Outputs, both [n_chunks][d] float32:
  *   mean_part[c][p]  = (sum of the chunk's frames at p) / t_total
  *   noise_part[c][p] = Welch estimate of chunk c (0 where the chunk has < 256 frames)
- * tab_cos / tab_sin: [128][64] float32 folded Hann-windowed DFT tables for bins 65..128
- * (built by the host, see localmd_b200/_tables.py). */
-int pmd_stats_pass(const void* movie, int dtype, int64_t t_local, int64_t d, int64_t t_total,
-                   const float* tab_cos, const float* tab_sin, float* mean_part, float* noise_part,
-                   void* stream);
+ * tab: 772 float32 built by the host (localmd_b200/_tables.py: welch_fft_tables): the periodic Hann window
+ * [256], the FFT twiddles (cos, -sin)(2 pi j/128) [128][2] and the split twiddles (cos, sin)(2 pi k/256)
+ * [130][2] (entries 129 unused). */
+int pmd_stats_pass(const void* movie, int dtype, int64_t t_local, int64_t d, int64_t t_total, const float* tab,
+                   float* mean_part, float* noise_part, void* stream);
 
 /* gather + standardise frames: out[i][p] = (movie[frames[i]][p] - mean[p]) / stdv[p]  (float32).
  * replaces: pmd_loader.py:293-298 (temporal_crop_standardized) and the first two lines of
@@ -177,6 +177,20 @@ int pmd_project_stream(const void* movie, int dtype, int64_t t, int64_t d2, int6
                        int64_t n_items, const int32_t* slot_ptr, const int32_t* tasks, int64_t max_rw,
                        const float* upack, const float* mean, const float* inv_std, float* z, int64_t ldz,
                        float* zbg, int64_t ldzbg, int64_t bg_stride, void* stream);
+
+/* HOST function (every pointer is a HOST pointer, no device work): builds the items / slot_ptr / tasks tables of
+ * pmd_project_stream from the block grid (row_starts x col_starts, blocks numbered row-major), the kept ranks and
+ * first output columns of the blocks and the number of dense background columns.  g_fixed > 0 forces that many block
+ * columns per strip, otherwise the strip width minimising the streamed pixels is chosen.  Outputs are caller
+ * allocated: items [cap_items][8], slot_ptr [cap_items*9], tasks [cap_tasks][12], local8 / local4 [cap_tasks][2]
+ * int64 (first column, n comps) in the order their U values must be packed, counts[8] = (n_items, n_slot_ptr, n_tasks,
+ * n_local8, n_local4, n_parts, max strip width, floats of the U pack); counts[0] == 0: geometry not supported.
+ * replaces: nothing in the reference (host bookkeeping of the new projection kernel). */
+int pmd_make_strips(const int32_t* row_starts, int64_t nbr, const int32_t* col_starts, int64_t nbc, int64_t bh,
+                    int64_t bw, int64_t d1, int64_t d2, const int64_t* ranks, const int64_t* col0, int64_t n_bg,
+                    int64_t g_fixed, int32_t* items_out, int64_t cap_items, int32_t* slot_ptr_out,
+                    int32_t* tasks_out, int64_t cap_tasks, int64_t* local8_out, int64_t* local4_out,
+                    int64_t* counts);
 
 /* K7b  full-movie projection onto dense (background) columns:
  *   z[c][f] += sum_p basis[c][p] * (movie[f][p] - mean[p]) * inv_std[p]     (c < k <= 16)

@@ -320,7 +320,7 @@ class SparseU:
         self.bg = bg  # (K, d) float32
         self.n_local = int(ranks_host.sum())
         self.n_cols = self.n_local + bg.shape[0]
-        self.tasks = torch.from_numpy(ops.make_tasks(ranks_host)).to(ranks_dev.device)
+        self._tasks = None
         self._csr = None
         self.supertiles = None
         self.strips = None
@@ -340,6 +340,12 @@ class SparseU:
                 if st["max_h"] * st["max_w"] <= 2048:
                     self.supertiles = {k: (torch.from_numpy(v).to(ranks_dev.device) if isinstance(v, np.ndarray) else v)
                                        for k, v in st.items()}
+
+    @property
+    def tasks(self):
+        if self._tasks is None:
+            self._tasks = torch.from_numpy(ops.make_tasks(self.ranks_host)).to(self.ranks_dev.device)
+        return self._tasks
 
     def coo_physical(self):
         """(rows = physical pixel ids, cols, float64 values) of all stored entries, exact zeros dropped
@@ -714,9 +720,14 @@ def localmd_decomposition(
         tm.mark("blocks")
 
         # ---- weighted sparse assembly (decomposition.py:811-857) -----------------------------------
-        cumw = np.zeros((d1, d2), dtype=np.float64)
-        for k, j in starts:
-            cumw[k : k + bh, j : j + bw] += block_weights
+        # summed pyramid weights of the covering blocks: sum_b shift(block_weights) = Rm^T W Cm with the 0/1
+        # incidence matrices of (block-local row, FOV row) and (block-local column, FOV column); exact in float64
+        rm, cm = np.zeros((bh, d1)), np.zeros((bw, d2))
+        for q in range(bh):
+            rm[q, np.asarray(dim_1_iters) + q] = 1.0
+        for q in range(bw):
+            cm[q, np.asarray(dim_2_iters) + q] = 1.0
+        cumw = rm.T @ block_weights.astype(np.float64) @ cm
         su = _assemble(u_blk, starts, starts_dev, bh, bw, d1, d2, ranks_host, ranks_dev, block_weights, cumw, bg)
         blk_of_col = torch.repeat_interleave(torch.arange(nb, device=dev), ranks_dev.to(torch.int64))
         comp_of_col = torch.arange(su.n_local, device=dev) - su.col0_dev[blk_of_col]
@@ -794,13 +805,21 @@ def project_movie(movie: DeviceMovie, su: SparseU, p, mean, inv_std):
     dev = movie.device
     k = p.shape[1]
     v_full = torch.empty((k, movie.n_local), dtype=torch.float32, device=dev)
-    pt = p.t().contiguous()
+    # the contraction dimension (columns of U) is padded to a multiple of 8 so that both GEMM operands have
+    # 16-byte aligned rows (tensor-core kernels need it); the padding rows / columns are zero
+    rpad = (su.n_cols + 7) // 8 * 8
+    pt = torch.zeros((k, rpad), dtype=torch.float32, device=dev)
+    pt[:, : su.n_cols] = p.t()
     for f0, chunk in movie.batches():
         n = chunk.shape[0]
-        z = torch.empty((su.n_cols, n), dtype=torch.float32, device=dev)
-        su.project(chunk, mean, inv_std, z)
+        npad = (n + 3) // 4 * 4
+        z = torch.empty((rpad, npad), dtype=torch.float32, device=dev)
+        z[su.n_cols :].zero_()
+        if npad != n:
+            z[:, n:].zero_()
+        su.project(chunk, mean, inv_std, z[: su.n_cols])
         _submark("projection.spmm")
-        v_full[:, f0 : f0 + n].copy_(torch.matmul(pt, z))
+        v_full[:, f0 : f0 + n].copy_(ops.matmul_3xtf32(pt, z)[:, :n])
         _submark("projection.mix")
         del z
     return v_full

@@ -9,7 +9,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._tables import welch_tables
+from ._tables import welch_fft_tables
 
 PMD_DTYPES = {
     torch.float32: 0,
@@ -64,8 +64,7 @@ _table_cache = {}
 def _tables(device):
     key = str(device)
     if key not in _table_cache:
-        tc, ts = welch_tables()
-        _table_cache[key] = (torch.from_numpy(tc).to(device), torch.from_numpy(ts).to(device))
+        _table_cache[key] = torch.from_numpy(welch_fft_tables()).to(device)
     return _table_cache[key]
 
 
@@ -84,8 +83,8 @@ def stats_pass(movie2d, t_total):
     n_chunks = (t_local + 1023) // 1024
     mean_part = torch.empty((n_chunks, d), dtype=torch.float32, device=movie2d.device)
     noise_part = torch.empty((n_chunks, d), dtype=torch.float32, device=movie2d.device)
-    tc, ts = _tables(movie2d.device)
-    _call("pmd_stats_pass", _p(movie2d), movie_dtype_code(movie2d), t_local, d, t_total, _p(tc), _p(ts), _p(mean_part),
+    tab = _tables(movie2d.device)
+    _call("pmd_stats_pass", _p(movie2d), movie_dtype_code(movie2d), t_local, d, t_total, _p(tab), _p(mean_part),
           _p(noise_part), _stream())
     n_var = sum(1 for c in range(n_chunks) if min(1024, t_local - 1024 * c) >= 256)
     return mean_part, noise_part, n_var
@@ -168,6 +167,29 @@ def standardize_frames_t(movie2d, frames, mean, stdv, ld=None):
     out = torch.empty((d, ld), dtype=torch.float32, device=movie2d.device)
     _call("pmd_standardize_frames_t", _p(movie2d), movie_dtype_code(movie2d), d, _p(frames), n, _p(mean), _p(stdv), _p(out), ld,
           _stream())
+    return out
+
+
+def _split_tf32(x):
+    """x = hi + lo with hi exactly representable in TF32 (10 mantissa bits, round to nearest)."""
+    hi = ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+    return hi, x - hi
+
+
+def matmul_3xtf32(a, b):
+    """float32-accurate a @ b on the tensor cores: three TF32 library GEMMs on split operands
+    (a_hi b_hi + a_lo b_hi + a_hi b_lo; the dropped a_lo b_lo term is ~2^-22 relative).  Used for the mixing GEMM
+    P^T (U^T Y) of pmd_loader.py:411-412."""
+    a_hi, a_lo = _split_tf32(a.contiguous())
+    b_hi, b_lo = _split_tf32(b.contiguous())
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        out = torch.matmul(a_hi, b_lo)
+        out.addmm_(a_lo, b_hi)
+        out.addmm_(a_hi, b_hi)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
     return out
 
 
@@ -497,8 +519,9 @@ def _pack_passes(tasks, n_slots):
     return out
 
 
-def make_strips(row_starts, col_starts, bh, bw, d1, d2, ranks_host, col0_host, n_bg, G=None):
-    """Host tables for pmd_project_stream (see include/pmd_sm100.h).  Blocks form the grid row_starts x col_starts
+def make_strips_py(row_starts, col_starts, bh, bw, d1, d2, ranks_host, col0_host, n_bg, G=None):
+    """Pure-Python twin of make_strips (pmd_make_strips), kept as the executable specification for the tests.
+    Host tables for pmd_project_stream (see include/pmd_sm100.h).  Blocks form the grid row_starts x col_starts
     (numbered row-major).  Returns a dict with int32 arrays items [n,8], slot_ptr, tasks [m,12], the order in which
     local tasks must be packed (`local8`, `local4`: arrays of (first column, n comps)), the background groups,
     `n_parts` and `max_rw`; or None when a single block column is already wider than the kernel's strip limit."""
@@ -589,6 +612,40 @@ def make_strips(row_starts, col_starts, bh, bw, d1, d2, ranks_host, col0_host, n
                 local4=np.array(local4, dtype=np.int64).reshape(-1, 2), bg_groups=bg_groups, upack_floats=off,
                 n_parts=1 + max(i["bg_part"] for i in items),
                 max_rw=max(i["rw"] for i in items), n_items=len(items))
+
+
+def _np_ptr(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+def make_strips(row_starts, col_starts, bh, bw, d1, d2, ranks_host, col0_host, n_bg, G=None):
+    """Host tables for pmd_project_stream, built by the native host routine pmd_make_strips (same result as
+    make_strips_py).  Returns the same dict, or None when the geometry is not supported by the kernel."""
+    rs = np.ascontiguousarray(row_starts, dtype=np.int32)
+    cs = np.ascontiguousarray(col_starts, dtype=np.int32)
+    ranks = np.ascontiguousarray(ranks_host, dtype=np.int64).reshape(-1)
+    col0 = np.ascontiguousarray(col0_host, dtype=np.int64).reshape(-1)
+    n_bg = int(n_bg)
+    n_groups = (n_bg + 7) // 8
+    cap_tasks = int(((ranks + 7) // 8).sum()) + len(cs) * n_groups + 8
+    cap_items = len(cs) + cap_tasks
+    items = np.zeros((cap_items, 8), np.int32)
+    slot_ptr = np.zeros(cap_items * 9, np.int32)
+    tasks = np.zeros((cap_tasks, 12), np.int32)
+    local8 = np.zeros((cap_tasks, 2), np.int64)
+    local4 = np.zeros((cap_tasks, 2), np.int64)
+    counts = np.zeros(8, np.int64)
+    rc = _lib.lib().pmd_make_strips(_np_ptr(rs), len(rs), _np_ptr(cs), len(cs), int(bh), int(bw), int(d1), int(d2), _np_ptr(ranks),
+                                    _np_ptr(col0), n_bg, int(G or 0), _np_ptr(items), cap_items, _np_ptr(slot_ptr), _np_ptr(tasks),
+                                    cap_tasks, _np_ptr(local8), _np_ptr(local4), _np_ptr(counts))
+    _lib.check(rc, "pmd_make_strips")
+    n_items, n_sp, n_tasks, n8, n4, n_parts, max_rw, upack_floats = (int(x) for x in counts)
+    if n_items == 0:
+        return None
+    return dict(items=items[:n_items].copy(), slot_ptr=slot_ptr[:n_sp].copy(), tasks=tasks[:n_tasks].copy(),
+                local8=local8[:n8].copy(), local4=local4[:n4].copy(),
+                bg_groups=[(k0, min(8, n_bg - k0)) for k0 in range(0, n_bg, 8)], upack_floats=upack_floats, n_parts=n_parts,
+                max_rw=max_rw, n_items=n_items)
 
 
 def pack_strip_u(st, uvals32, bg, bpix):

@@ -86,14 +86,17 @@ def test_task_tables():
 
 
 def test_welch_tables_identity():
-    from localmd_b200._tables import welch_from_tables_reference, welch_tables
+    """Both kernel formulations of the Welch estimate (folded tables, v1; FFT + real split, v2) equal scipy's welch."""
+    from localmd_b200._tables import welch_fft_reference, welch_fft_tables, welch_from_tables_reference, welch_tables
 
     tc, ts = welch_tables()
     assert tc.shape == (128, 64) and ts.shape == (128, 64) and tc.dtype == np.float32
+    assert welch_fft_tables().shape == (772,) and welch_fft_tables().dtype == np.float32
     rng = np.random.default_rng(0)
     for n in (1024, 544, 256, 300):
         x = (200 + 3 * rng.standard_normal((16, n))).astype(np.float32)
         np.testing.assert_allclose(welch_from_tables_reference(x), O.welch_noise_estimate(x), rtol=1e-6)
+        np.testing.assert_allclose(welch_fft_reference(x), O.welch_noise_estimate(x), rtol=1e-6)
 
 
 def test_npz_layout_and_pmdarray_container():
@@ -186,6 +189,11 @@ def test_strip_tables():
         ranks = rng.integers(1, hi + 1, len(rs) * len(cs))
         col0 = np.concatenate([[0], np.cumsum(ranks)[:-1]])
         st = host_ops.make_strips(rs, cs, bh, bw, d1, d2, ranks, col0, n_bg)
+        ref = host_ops.make_strips_py(rs, cs, bh, bw, d1, d2, ranks, col0, n_bg)  # native builder == Python specification
+        for key in ("items", "slot_ptr", "tasks", "local8", "local4"):
+            assert np.array_equal(st[key], ref[key]), key
+        assert (st["upack_floats"], st["n_parts"], st["max_rw"], st["n_items"]) == (
+            ref["upack_floats"], ref["n_parts"], ref["max_rw"], ref["n_items"])
         items, slot_ptr, tasks = st["items"], st["slot_ptr"], st["tasks"]
         assert st["max_rw"] <= host_ops.PS_MAX_RW
         seen_cols = np.zeros(int(ranks.sum()), int)

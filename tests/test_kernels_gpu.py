@@ -100,6 +100,16 @@ def test_orthonormalize_rank_deficient(ops):
         assert np.abs(proj - a[b]).max() < 1e-4  # span contains the original columns
 
 
+def test_matmul_3xtf32(ops):
+    rng = np.random.default_rng(1)
+    a = (rng.standard_normal((300, 1000)) * np.exp(rng.uniform(-8, 8, (300, 1)))).astype(np.float32)
+    b = (rng.standard_normal((1000, 700)) * np.exp(rng.uniform(-8, 8, (1, 700)))).astype(np.float32)
+    got = ops.matmul_3xtf32(dev(a), dev(b)).cpu().numpy().astype(np.float64)
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    scale = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+    assert np.max(np.abs(got - ref) / scale) < 2e-6  # float32-class accuracy (plain TF32 would be ~1e-3)
+
+
 @pytest.mark.parametrize("m,n,ld,rank", [(100, 60, 60, 60), (400, 50, 52, 50), (400, 50, 52, 17), (144, 11, 11, 11), (30, 8, 12, 5)])
 def test_block_orth(ops, m, n, ld, rank):
     """Fused CholQR2: orthonormal columns spanning the input's column space; dependent columns dropped."""

@@ -52,7 +52,9 @@ project_stream_kernel(const T* __restrict__ movie, int64_t t, int64_t tile0, int
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const PSItem it = items[blockIdx.x];
     const int rw = it.rw, c0 = it.c0, row0 = it.row0, row_end = it.row0 + it.n_rows;
-    const int64_t f0 = (tile0 + blockIdx.y) * kPSF;
+    // the last tile is shifted back so that it is full (it recomputes, and rewrites with identical values, a few
+    // frames of its neighbour); only movies shorter than one tile take the clamped FULL = false path
+    const int64_t f0 = FULL ? min((tile0 + blockIdx.y) * kPSF, t - kPSF) : (tile0 + blockIdx.y) * kPSF;
     const int xstride = rw * kPSF;
     float* const ubuf = sm + 2 * xstride + warp * (2 * kPSMaxRW * 8);   // two U slabs per warp
 
@@ -281,7 +283,7 @@ extern "C" int pmd_project_stream(const void* movie, int dtype, int64_t t, int64
     PMD_REQUIRE(ftiles <= 65535, fn, "too many frames per call");
     const size_t smem = (size_t)(2 * max_rw * pmd::kPSF + pmd::kPSWarps * 2 * pmd::kPSMaxRW * 8) * sizeof(float);
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t full_tiles = t / pmd::kPSF;
+    const int64_t full_tiles = t >= pmd::kPSF ? ftiles : 0;   // t >= 256: every tile is full (the last one overlaps)
 #define PMD_LAUNCH_PS(SETS, FULL, TILE0, NT)                                                                             \
     if ((NT) > 0) {                                                                                                      \
         auto k = pmd::project_stream_kernel<scalar_t, SETS, FULL>;                                                       \

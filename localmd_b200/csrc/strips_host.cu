@@ -134,7 +134,9 @@ bool build(int g, const int32_t* rs, int nbr, const int32_t* cs, int nbc, int bh
             }
         const size_t before = items.size();
         pack_passes(std::move(tasks), items, c0, c1 - c0, part);
-        for (size_t i = before; i < items.size(); ++i) streamed += (long)items[i].rw * (items[i].row1 - items[i].row0);
+        // cost of a pass: rows x staged lanes (the kernel stages pixels in sets of 32 lanes)
+        for (size_t i = before; i < items.size(); ++i)
+            streamed += (long)((items[i].rw + 31) / 32 * 32) * (items[i].row1 - items[i].row0);
     }
     return true;
 }

@@ -557,7 +557,7 @@ def make_strips_py(row_starts, col_starts, bh, bw, d1, d2, ranks_host, col0_host
             loc.sort(key=lambda x: x[0])
             for (row0, row1, slots) in _pack_passes(tasks + loc, PS_WARPS):
                 items.append(dict(c0=c0, rw=c1 - c0, slots=slots, bg_part=part, row0=row0, n_rows=row1 - row0))
-                total_rw += (c1 - c0) * (row1 - row0)
+                total_rw += ((c1 - c0 + 31) // 32 * 32) * (row1 - row0)
         return items, total_rw
 
     best = None

@@ -178,15 +178,18 @@ def workload_config(name, n_gpus):
     w = WORKLOADS[name]
     return {"workload": "synthetic %dx%dx%d float32 two-photon movie, block %dx%d, frames_to_init %d, rank_prune 0.33 "
                         "(BASELINE.json configs[1])" % (w["d1"], w["d2"], w["T"], w["block"], w["block"], w["frames_to_init"]),
-            "frames_per_gpu": w["T"], "timing": "inputs (21 GB/GPU) larger than L2; CUDA events, max over ranks",
-            "parallelism": "frame-sharded x%d" % n_gpus if n_gpus > 1 else "single GPU"}
+            "frames_per_gpu": w["T"], "total_frames": w["T"] * n_gpus,
+            "timing": "inputs (21 GB/GPU) larger than L2; CUDA events, max over ranks",
+            "parallelism": "one movie of %d frames, frame-sharded x%d (blocks partitioned, NCCL reductions/gathers)"
+                           % (w["T"] * n_gpus, n_gpus) if n_gpus > 1 else "single GPU"}
 
 
 def run_ours(args):
     import torch
 
     import localmd_b200
-    from localmd_b200 import ops
+    from localmd_b200 import ops, sharding
+    from localmd_b200.dataset import DeviceMovie
     from localmd_b200.synthetic import make_movie
 
     rank = int(os.environ.get("RANK", "0"))
@@ -194,25 +197,32 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    group = None
     if world > 1:
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
     w = WORKLOADS[args.workload]
     T, d1, d2, blk, t_init = w["T"], w["d1"], w["d2"], w["block"], w["frames_to_init"]
-    # weak scaling: every rank compresses its own movie of the named shape (the path shards by frames with
-    # no data-path collective in this round; see DESIGN.md section "multi-GPU")
-    movie = make_movie(T, d1, d2, n_cells=w["n_cells"], blob_sigma=w["blob"], bg_rank=w["bg_rank"], seed=1234 + rank, device=dev)
-    kw = dict(block_sizes=[blk, blk], frame_range=t_init, rank_prune=True, seed=0)
+    # weak scaling: ONE movie of world * T frames, frame-sharded over the ranks (1024-aligned contiguous ranges);
+    # the stats and projection passes run on the local shard, the block stage is partitioned by blocks, the rank-sized
+    # reductions / gathers go over NCCL (DESIGN.md section "multi-GPU")
+    t_total = world * T
+    lo, hi = sharding.shard_bounds(t_total, world)[rank]
+    shard = make_movie(t_total, d1, d2, n_cells=w["n_cells"], blob_sigma=w["blob"], bg_rank=w["bg_rank"], seed=1234, device=dev,
+                       frame_lo=lo, frame_hi=hi)
+    movie = DeviceMovie.from_shard(shard, t_total, lo)
+    kw = dict(block_sizes=[blk, blk], frame_range=t_init, rank_prune=True, seed=0, group=group)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    stage = {"__detail__": True} if args.stage_times else {}
+    stage = {"__detail__": True}
     for i in range(args.warmup):
-        localmd_b200.localmd_decomposition(movie, timings=stage if (args.stage_times and i == args.warmup - 1) else None, **kw)
+        localmd_b200.localmd_decomposition(movie, timings=stage if i == args.warmup - 1 else None, **kw)
     if args.stage_times and rank == 0:
         sys.stderr.write("stage ms: %s\n" % json.dumps({k: round(v, 2) for k, v in stage.items() if isinstance(v, float)}))
         sys.stderr.write("n_cols/ranks info: %s\n" % json.dumps(stage.get("__info__", {})))
@@ -221,14 +231,13 @@ def run_ours(args):
     if rank == 0:
         sampler.start()
     n0 = ops.LAUNCHES["count"]
-    names0 = dict(ops.LAUNCHES["by_name"])
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    proj_ms = []
+    per_step = []
     ev0.record()
     for _ in range(args.steps):
-        tms = {}
+        tms = {"__detail__": True}
         localmd_b200.localmd_decomposition(movie, timings=tms, **kw)
-        proj_ms.append(tms)
+        per_step.append(tms)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -239,38 +248,51 @@ def run_ours(args):
         dist.all_reduce(tms_t, op=dist.ReduceOp.MAX)
         ms = float(tms_t.item())
     ms_step = ms / args.steps
-    value = world * T / (ms_step / 1e3)
+    value = t_total / (ms_step / 1e3)
 
-    # roofline of the dominant streaming kernel pair (K7 projection pass), from the per-stage CUDA events
+    # roofline of the dominant streaming kernel (K7 = pmd_project_stream): algorithmic bytes = every movie element
+    # of the local shard read once + the Z rows written once, over the kernel's own CUDA-event time
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    proj = float(np.mean([p["projection"] for p in proj_ms]))
-    k_final = 1650
-    alg_bytes = 4.0 * d1 * d2 * T + 4.0 * k_final * T
-    achieved = alg_bytes / (proj / 1e3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "projection pass (pmd_project_local + pmd_project_dense + mixing GEMM)",
+    info = per_step[-1].get("__info__", {})
+    n_cols = int(info.get("n_cols", 0))
+    k7_ms = float(np.mean([p["projection.stream"] for p in per_step]))
+    pass_ms = float(np.mean([p["projection"] for p in per_step]))
+    n_loc = hi - lo
+    alg_bytes = 4.0 * d1 * d2 * n_loc + 4.0 * n_cols * n_loc
+    achieved = alg_bytes / (k7_ms / 1e3) / 1e9
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "k7_traffic.json")))
+        if tr.get("workload") == args.workload:
+            traffic = tr.get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": "pmd_project_stream (K7: U^T standardised movie, local + background columns)",
                 "achieved": achieved, "peak": peak, "peak_source": "measured" if peaks else "fallback", "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "ms": proj}
+                "frac": achieved / peak, "traffic": traffic, "ms": k7_ms, "algorithmic_bytes": alg_bytes,
+                "projection_pass_ms": pass_ms, "n_cols": n_cols}
 
     e2e = None
     if not args.no_e2e:
-        host = movie.cpu().numpy()
-        host_t = torch.from_numpy(host).pin_memory()
-        host_np = host_t.numpy()
-        del movie
+        host_t = torch.empty(shard.shape, dtype=shard.dtype, pin_memory=True)
+        host_t.copy_(shard)
+        del movie, shard
         torch.cuda.empty_cache()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record()
         det = {}
-        arr = localmd_b200.localmd_decomposition(host_np, timings=det, **kw)
-        result = (arr.u, arr.r, arr.s, arr.v, arr.mean_img, arr.var_img)  # device -> host read of the compressed movie
-        frame = arr[T // 2, :, :]  # ... and of one reconstructed frame
+        src = host_t.numpy() if world == 1 else DeviceMovie.from_host_shard(host_t, t_total, lo, dev)
+        arr = localmd_b200.localmd_decomposition(src, timings=det, **kw)
+        if rank == 0:
+            result = (arr.u, arr.r, arr.s, arr.v, arr.mean_img, arr.var_img)  # device -> host read of the compressed movie
+            frame = arr[t_total // 2, :, :]  # ... and of one reconstructed frame
         e1.record()
         barrier()
         wall = time.perf_counter() - t0
@@ -279,13 +301,16 @@ def run_ours(args):
             tt = torch.tensor([e2e_ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_ms = float(tt.item())
-        d2h = int(arr.u.data.nbytes + arr.u.indices.nbytes + arr.u.indptr.nbytes + arr.r.nbytes + arr.s.nbytes + arr.v.nbytes
-                  + 2 * 4 * d1 * d2 + frame.nbytes)
-        del result
-        e2e = {"value": world * T / (e2e_ms / 1e3), "unit": "frames/s",
-               "h2d_bytes_per_step": int(det.get("__info__", {}).get("h2d_bytes", host.nbytes)),
-               "d2h_bytes_per_step": d2h, "ms": e2e_ms}
+        if rank == 0:
+            d2h = int(arr.u.data.nbytes + arr.u.indices.nbytes + arr.u.indptr.nbytes + arr.r.nbytes + arr.s.nbytes + arr.v.nbytes
+                      + 2 * 4 * d1 * d2 + frame.nbytes)
+            del result
+            e2e = {"value": t_total / (e2e_ms / 1e3), "unit": "frames/s",
+                   "h2d_bytes_per_step": int(det.get("__info__", {}).get("h2d_bytes", host_t.numel() * host_t.element_size())) * world,
+                   "d2h_bytes_per_step": d2h, "ms": e2e_ms}
 
+    if world > 1:
+        dist.destroy_process_group()
     if rank != 0:
         return
     line = {
@@ -293,9 +318,10 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, world), "clocks": clocks,
         "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
-        "stage_ms": {k: round(float(np.mean([p[k] for p in proj_ms])), 3) for k in proj_ms[0] if isinstance(proj_ms[0][k], float)},
+        "stage_ms": {k: round(float(np.mean([p[k] for p in per_step])), 3) for k in per_step[0]
+                     if isinstance(per_step[0][k], float) and "." not in k},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         scaled, raw, sample, cores, _ = cpu_reference_sample(w)
         line["cpu_baseline"] = {"value": scaled, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
                                 "sample_frames_per_s": raw}

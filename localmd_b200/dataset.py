@@ -149,6 +149,7 @@ class DeviceMovie:
         self._resident = None
         self._filled = True
         self._host2d = None
+        self._host_off = 0
         self._staging = None
         if isinstance(dataset_obj, torch.Tensor):
             if not dataset_obj.is_cuda:
@@ -182,6 +183,45 @@ class DeviceMovie:
         if nbytes <= resident_fraction * free:
             self._resident = torch.empty((self.hi - self.lo, self.d), dtype=self.torch_dtype, device=self.device)
             self._filled = False
+
+    @classmethod
+    def from_shard(cls, local, n_frames_total, frame_lo):
+        """Wrap this rank's frame shard `local` (n_local, d1, d2), a CUDA tensor of a supported dtype holding frames
+        [frame_lo, frame_lo + n_local) of a movie with n_frames_total frames (multi-GPU: one shard per rank)."""
+        if not (isinstance(local, torch.Tensor) and local.is_cuda):
+            raise TypeError("from_shard expects a CUDA tensor")
+        self = cls.__new__(cls)
+        self.device = local.device
+        self.T_total = int(n_frames_total)
+        self.d1, self.d2 = int(local.shape[1]), int(local.shape[2])
+        self.d = self.d1 * self.d2
+        self.lo, self.hi = int(frame_lo), int(frame_lo) + int(local.shape[0])
+        self.batch_frames = self.upload_frames = 2048
+        self.h2d_bytes = 0
+        self._src = None
+        t = local if local.dtype in ops.PMD_DTYPES else local.to(torch.float32)
+        self._resident = t.contiguous().view(self.hi - self.lo, self.d)
+        self.torch_dtype = t.dtype
+        self._filled = True
+        self._host2d = None
+        self._staging = None
+        return self
+
+    @classmethod
+    def from_host_shard(cls, local, n_frames_total, frame_lo, device, **kw):
+        """This rank's frame shard as a HOST array / CPU tensor (n_local, d1, d2) holding frames
+        [frame_lo, frame_lo + n_local) of a movie with n_frames_total frames; uploaded like any host dataset."""
+        n = int(local.shape[0])
+        self = cls.__new__(cls)
+        proxy = torch.from_numpy(local) if isinstance(local, np.ndarray) else local
+        if proxy.dtype not in ops.PMD_DTYPES or not proxy.is_contiguous():
+            proxy = proxy.to(torch.float32).contiguous()
+        cls.__init__(self, proxy, device, frame_lo=0, frame_hi=n, **kw)  # as a stand-alone movie of n frames ...
+        # ... then re-labelled with its global frame range
+        self.T_total = int(n_frames_total)
+        self.lo, self.hi = int(frame_lo), int(frame_lo) + n
+        self._host_off = int(frame_lo)
+        return self
 
     @property
     def n_local(self):
@@ -221,12 +261,12 @@ class DeviceMovie:
         n = f1 - f0
         with torch.cuda.stream(self._copy_stream):
             if self._host2d is not None and self._pinned_src:
-                dst.copy_(self._host2d[f0:f1], non_blocking=True)
+                dst.copy_(self._host2d[f0 - self._host_off : f1 - self._host_off], non_blocking=True)
                 slot = None
             else:
                 slot, buf = self._stage(n)
                 if self._host2d is not None:
-                    buf.copy_(self._host2d[f0:f1])
+                    buf.copy_(self._host2d[f0 - self._host_off : f1 - self._host_off])
                 else:
                     arr = np.asarray(self._src[list(range(f0, f1))])
                     arr = arr[None] if arr.ndim == 2 else arr
@@ -298,7 +338,7 @@ class DeviceMovie:
             idx = torch.as_tensor(ids, dtype=torch.int64, device=self._src.device)
             return _index_rows(self._src.view(self.T_total, self.d), idx).to(self.device)
         if self._host2d is not None:
-            idx = torch.as_tensor(ids, dtype=torch.int64)
+            idx = torch.as_tensor(ids, dtype=torch.int64) - self._host_off
             host = _index_rows(self._host2d, idx)
             self.h2d_bytes += host.numel() * host.element_size()
             return host.to(self.device)

@@ -20,7 +20,7 @@ import numpy as np
 import scipy.sparse
 import torch
 
-from . import ops
+from . import ops, sharding
 from .dataset import DeviceMovie
 from .pmdarray import PMDArray
 
@@ -186,10 +186,11 @@ def compute_mean_and_noise(movie: DeviceMovie, compute_normalizer=True, group=No
     return mean, std
 
 
-def background_basis(movie: DeviceMovie, mean, std, bg_frames, bg_sketch, background_rank):
-    """pmd_loader.py:300-314 + 46-68: rSVD of <= 1000 standardised frames -> (K, d) orthonormal rows."""
+def background_basis(movie: DeviceMovie, mean, std, bg_frames, bg_sketch, background_rank, group=None, bounds=None):
+    """pmd_loader.py:300-314 + 46-68: rSVD of <= 1000 standardised frames -> (K, d) orthonormal rows.
+    With a process group the sampled frames are fetched from their owner ranks; every rank computes the same basis."""
     dev = movie.device
-    raw = movie.gather(bg_frames)
+    raw = sharding.gather_frames(movie, bg_frames, group, bounds)
     a_t = ops.standardize_frames(raw, torch.arange(raw.shape[0], device=dev), mean, std)  # (n, d) = A^T
     y = torch.matmul(a_t.t(), bg_sketch).contiguous()  # (d, l)
     q = ops.orthonormalize_cols(y[None])[0]  # (d, l)
@@ -437,7 +438,7 @@ class SparseU:
         n = movie2d.shape[0]
         if self.strips is not None:
             ops.project_stream(movie2d, self.d2, self.strips, self.upack, mean, inv_std, z[: self.n_local], z[self.n_local :])
-            _submark("project.stream")
+            _submark("projection.stream")
             return
         if self.n_local > 0:
             if self.supertiles is not None:
@@ -448,7 +449,7 @@ class SparseU:
                     z[: self.n_local, :n].zero_()
                 ops.project_local(movie2d, self.d2, self.starts_dev, self.bh, self.bw, self.ranks_dev, self.col0_dev,
                                   self.tasks, self.uvals32, mean, inv_std, z[: self.n_local])
-            _submark("project.local")
+            _submark("projection.local")
         zb = z[self.n_local :]
         zb[:, :n].zero_()
         ops.project_dense(movie2d, self.bg, mean, inv_std, zb)
@@ -587,6 +588,7 @@ def localmd_decomposition(
     timings: Optional[dict] = None,
     details: Optional[dict] = None,
     verbose: bool = False,
+    group=None,
 ):
     if block_sizes is None:
         if block_height is None or block_width is None:
@@ -619,12 +621,28 @@ def localmd_decomposition(
         tm = _Timer(timings, dev)
         _ACTIVE_TIMER = tm
         tm.mark("start")
-        movie = dataset_obj if isinstance(dataset_obj, DeviceMovie) else DeviceMovie(dataset_obj, dev, batch_frames=max(1024, frame_batch_size))
+        # ---- frame sharding (group = torch.distributed process group, one rank per GPU) ------------
+        rank, world = sharding.dist_info(group)
+        if isinstance(dataset_obj, DeviceMovie):
+            movie = dataset_obj
+        elif group is None:
+            movie = DeviceMovie(dataset_obj, dev, batch_frames=max(1024, frame_batch_size))
+        else:
+            lo, hi = sharding.shard_bounds(T, world)[rank]
+            movie = DeviceMovie(dataset_obj, dev, batch_frames=max(1024, frame_batch_size), frame_lo=lo, frame_hi=hi)
+        bounds = None
+        if group is not None:
+            import torch.distributed as dist
+
+            mine = torch.tensor([movie.lo, movie.hi], dtype=torch.int64, device=dev)
+            allb = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(allb, mine, group=group)
+            bounds = [(int(b[0]), int(b[1])) for b in torch.stack(allb).cpu()]
         tm.mark("upload")
 
         # ---- PMDLoader.__init__ : normalisers + background (pmd_loader.py:172-173) --------------
         say("Computing Video Statistics")
-        mean, std = compute_mean_and_noise(movie, compute_normalizer)
+        mean, std = compute_mean_and_noise(movie, compute_normalizer, group)
         inv_std = 1.0 / std
         tm.mark("stats")
         if background_rank > 0:
@@ -638,7 +656,7 @@ def localmd_decomposition(
                 if bg_sketch is not None
                 else torch.randn((len(bg_frames), background_rank + 10), generator=gen, device=dev, dtype=torch.float32)
             )
-            bg = background_basis(movie, mean, std, bg_frames, bg_sketch, background_rank)
+            bg = background_basis(movie, mean, std, bg_frames, bg_sketch, background_rank, group, bounds)
         else:
             bg = torch.zeros((1, d), dtype=torch.float32, device=dev)
         tm.mark("background")
@@ -690,7 +708,11 @@ def localmd_decomposition(
             raise ValueError("max_components > 102 is not supported by the sm_100a Jacobi kernel")
         if r > 64:
             raise ValueError("max_components > 64 is not supported by the sm_100a block kernels")
-        src2d, idx = movie.frame_source(frames[:crop])
+        if group is None:
+            src2d, idx = movie.frame_source(frames[:crop])
+        else:  # the init window lives on its owner rank(s): every rank receives the raw frames
+            src2d = sharding.gather_frames(movie, frames[:crop], group, bounds)
+            idx = torch.arange(src2d.shape[0], dtype=torch.int64, device=dev)
         yt = ops.standardize_frames_t(src2d, idx, mean, std)  # (d, ld)
         del src2d, idx
         vbg = torch.matmul(bg, yt).contiguous()  # (K, ld)
@@ -711,11 +733,21 @@ def localmd_decomposition(
             sketches = torch.stack([_as_dev(b_[0] if isinstance(b_, (list, tuple)) else b_, dev) for b_ in bs])
         else:
             sketches = torch.randn((nb, crop // temporal_avg_factor, r + 10), generator=gen, device=dev, dtype=torch.float32)
-        u_blk, v_blk, ranks_dev, sstat, tstat = block_decompositions(
-            yt, crop, d2, starts_dev, bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
-            int(max_consecutive_failures), sketches,
+        # blocks are partitioned over the ranks (contiguous index ranges); results are all-gathered below
+        b0, b1 = sharding.block_partition(nb, world)[rank]
+        u_blk, v_blk, ranks_loc, sstat, tstat = block_decompositions(
+            yt, crop, d2, starts_dev[b0:b1], bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
+            int(max_consecutive_failures), sketches[b0:b1],
         )
         del sketches
+        if group is None:
+            ranks_dev = ranks_loc
+        else:
+            bcounts = [hi_ - lo_ for lo_, hi_ in sharding.block_partition(nb, world)]
+            ranks_dev = sharding.ragged_all_gather(ranks_loc.contiguous(), bcounts, group)
+            if details is not None:
+                sstat = sharding.ragged_all_gather(sstat.contiguous(), bcounts, group)
+                tstat = sharding.ragged_all_gather(tstat.contiguous(), bcounts, group)
         ranks_host = ranks_dev.cpu().numpy().astype(np.int64)
         tm.mark("blocks")
 
@@ -728,11 +760,26 @@ def localmd_decomposition(
         for q in range(bw):
             cm[q, np.asarray(dim_2_iters) + q] = 1.0
         cumw = rm.T @ block_weights.astype(np.float64) @ cm
-        su = _assemble(u_blk, starts, starts_dev, bh, bw, d1, d2, ranks_host, ranks_dev, block_weights, cumw, bg)
-        blk_of_col = torch.repeat_interleave(torch.arange(nb, device=dev), ranks_dev.to(torch.int64))
-        comp_of_col = torch.arange(su.n_local, device=dev) - su.col0_dev[blk_of_col]
-        v_init = torch.cat([v_blk[blk_of_col, comp_of_col][:, :crop], vbg[:, :crop]], dim=0)  # (R, t)
+        # this rank's kept components: weighted values (float64 + float32) and temporal traces
+        ranks_loc_host = ranks_host[b0:b1]
+        col0_loc = torch.from_numpy(np.concatenate([[0], np.cumsum(ranks_loc_host)[:-1]]).astype(np.int64)).to(dev)
+        ncol_loc = int(ranks_loc_host.sum())
+        uv64, uv32 = ops.assemble_u(
+            u_blk, bh, bw, starts_dev[b0:b1].contiguous(), ranks_loc, col0_loc, torch.from_numpy(block_weights.reshape(-1)).to(dev),
+            torch.from_numpy(cumw.reshape(-1)).to(dev), d2, ncol_loc,
+        )
+        blk_of_col = torch.repeat_interleave(torch.arange(b1 - b0, device=dev), ranks_loc.to(torch.int64))
+        comp_of_col = torch.arange(ncol_loc, device=dev) - col0_loc[blk_of_col]
+        v_loc = v_blk[blk_of_col, comp_of_col][:, :crop].contiguous()  # (local columns, t)
         del u_blk, v_blk, yt
+        if group is not None:
+            ccounts = [int(ranks_host[lo_:hi_].sum()) for lo_, hi_ in sharding.block_partition(nb, world)]
+            uv64 = sharding.ragged_all_gather(uv64, ccounts, group)
+            uv32 = sharding.ragged_all_gather(uv32, ccounts, group)
+            v_loc = sharding.ragged_all_gather(v_loc, ccounts, group)
+        su = SparseU(starts, starts_dev, bh, bw, d1, d2, ranks_host, ranks_dev, uv64, uv32, bg)
+        v_init = torch.cat([v_loc, vbg[:, :crop]], dim=0)  # (R, t)
+        del v_loc
         say("The total rank before pruning is {}".format(su.n_cols))
         if timings is not None:
             timings["__info__"] = dict(n_cols=int(su.n_cols), n_local=int(su.n_local), nb=int(nb), mean_rank=float(ranks_host.mean()),
@@ -763,9 +810,12 @@ def localmd_decomposition(
         tm.mark("projection")
 
         # ---- final SVD (decomposition.py:896-904) ---------------------------------------------------
-        rmix, s, vt = projected_svd(p, v_full)
+        rmix, s, vt = projected_svd(p, v_full, group)
         good = s != 0
         rmix, s, vt = rmix[:, good], s[good], vt[good, :]
+        if group is not None:  # Vt column shards -> the full (k, T) factor on every rank
+            fcounts = [hi_ - lo_ for lo_, hi_ in bounds]
+            vt = sharding.ragged_all_gather(vt.t().contiguous(), fcounts, group).t().contiguous()
         tm.mark("final_svd")
 
         # ---- result object ---------------------------------------------------------------------------
@@ -789,17 +839,6 @@ def localmd_decomposition(
         return out
 
 
-def _assemble(u_blk, starts, starts_dev, bh, bw, d1, d2, ranks_host, ranks_dev, block_weights, cumw, bg):
-    dev = u_blk.device
-    col0 = torch.from_numpy(np.concatenate([[0], np.cumsum(ranks_host)[:-1]]).astype(np.int64)).to(dev)
-    n_local = int(ranks_host.sum())
-    uv64, uv32 = ops.assemble_u(
-        u_blk, bh, bw, starts_dev, ranks_dev, col0, torch.from_numpy(block_weights.reshape(-1)).to(dev),
-        torch.from_numpy(cumw.reshape(-1)).to(dev), d2, n_local,
-    )
-    return SparseU(starts, starts_dev, bh, bw, d1, d2, ranks_host, ranks_dev, uv64, uv32, bg)
-
-
 def project_movie(movie: DeviceMovie, su: SparseU, p, mean, inv_std):
     """K7: V = P^T U^T ((Y - mean)/std) over this rank's frames -> (k, n_local) float32."""
     dev = movie.device
@@ -818,7 +857,7 @@ def project_movie(movie: DeviceMovie, su: SparseU, p, mean, inv_std):
         if npad != n:
             z[:, n:].zero_()
         su.project(chunk, mean, inv_std, z[: su.n_cols])
-        _submark("projection.spmm")
+        _submark("projection.dense")
         v_full[:, f0 : f0 + n].copy_(ops.matmul_3xtf32(pt, z)[:, :n])
         _submark("projection.mix")
         del z

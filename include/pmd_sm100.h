@@ -96,6 +96,12 @@ int pmd_block_orth(float* x, int64_t batch, int64_t m, int64_t n, int64_t ldx, c
 int pmd_block_pool_tavg(const float* yt, int64_t ld, int64_t t, int64_t d2, const int32_t* starts, int64_t nb,
                         int64_t bh, int64_t bw, int64_t saf, int64_t taf, float* bta, void* stream);
 
+/* same pooling, but ALSO keeps the pooled block at full time resolution:  pooled [nb][P][ld] (columns t..ld-1 zero)
+ * = B_ds of decomposition.py:279, so that U_ds^T B_ds (295-298) contracts over P pooled pixels (pmd_block_project
+ * with movie_batch_stride = P*ld, d2 = ceil(bw/saf), starts = 0).  t a multiple of taf. */
+int pmd_block_pool_full(const float* yt, int64_t ld, int64_t t, int64_t d2, const int32_t* starts, int64_t nb,
+                        int64_t bh, int64_t bw, int64_t saf, int64_t taf, float* pooled, float* bta, void* stream);
+
 /* spread a pooled spatial basis back to full resolution: w[b][q][c] = uds[b][pool(q)][c] / count(pool(q)),
  * so that w^T * block == uds^T * pooled(block)  (decomposition.py:295-298 without materialising the
  * pooled block).  uds: [nb][P][r], w: [nb][bh*bw][rp] (rp >= r, multiple of 4, padding zeroed). */

@@ -87,6 +87,52 @@ block_pool_tavg_t_kernel(const float* __restrict__ yT, int64_t ld, int64_t t, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// pooled block at full time resolution  pooled[b][p][f]  AND its time average  bta[b][p][tau]  in one pass
+// (decomposition.py:279 B_ds and 283-290 B_ta): a streaming pooling kernel (thread = frame) + a tiny averaging kernel.
+// The pooled tensor lets the first block projection (decomposition.py:295-298, U_ds^T B_ds) contract over the
+// P = bpix/4 pooled pixels instead of the bpix full-resolution ones.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+block_pool_full_kernel(const float* __restrict__ yT, int64_t ld, int64_t t, int64_t d2, const int32_t* __restrict__ starts,
+                       int bh, int bw, int saf, float* __restrict__ pooled) {
+    const int ph = (bh + saf - 1) / saf, pw = (bw + saf - 1) / saf;
+    const int lo_h = (ph * saf - bh) / 2, lo_w = (pw * saf - bw) / 2;
+    const int P = ph * pw;
+    const int64_t b = blockIdx.y;
+    const int i0 = starts[2 * b], j0 = starts[2 * b + 1];
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= ld) return;
+    const float* base = yT + ((int64_t)i0 * d2 + j0) * ld + f;
+    float* out = pooled + b * P * ld + f;
+#pragma unroll 4
+    for (int p = 0; p < P; ++p) {
+        const int pi = p / pw, pj = p - pi * pw;
+        const int r0 = max(pi * saf - lo_h, 0), r1 = min(pi * saf - lo_h + saf, bh);
+        const int c0 = max(pj * saf - lo_w, 0), c1 = min(pj * saf - lo_w + saf, bw);
+        float v = 0.f;
+        if (f < t) {
+            float sum = 0.f;
+            for (int r = r0; r < r1; ++r)
+                for (int c = c0; c < c1; ++c) sum += base[((int64_t)r * d2 + c) * ld];
+            v = sum / (float)((r1 - r0) * (c1 - c0));
+        }
+        out[(int64_t)p * ld] = v;
+    }
+}
+
+// bta[row][tau] = mean of pooled[row][tau*taf .. tau*taf+taf)   (rows = nb * P)
+__global__ void __launch_bounds__(256)
+block_tavg_kernel(const float* __restrict__ pooled, int64_t ld, int64_t nrows, int64_t tp, int taf, float* __restrict__ bta) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nrows * tp) return;
+    const int64_t row = idx / tp, tau = idx - row * tp;
+    const float* src = pooled + row * ld + tau * taf;
+    float acc = 0.f;
+    for (int ff = 0; ff < taf; ++ff) acc += src[ff];
+    bta[idx] = acc / (float)taf;
+}
+
+// ------------------------------------------------------------------------------------------------
 // out[b][c][f] = sum_q w[b][q][c] * yT[pix(b,q)][f]
 // CTA = (256 frames, block b, group of NG*8 components); warp g owns components 8g..8g+7, lane l owns
 // frames 4l..4l+3 and 128+4l..128+4l+3 of the tile.  K runs over the block's pixels in chunks of <= 16
@@ -111,25 +157,25 @@ block_project_t_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld, 
     const int i0 = starts[2 * b], j0 = starts[2 * b + 1];
     const float* mv = movT + b * mbs;
     const float* wb = w + b * (int64_t)(bh * bw) * rp;
-    const int segs = (bw + kPK - 1) / kPK;
-    const int nchunks = bh * segs;
+    const int bpix = bh * bw;
+    const int nchunks = (bpix + kPK - 1) / kPK;   // K chunks of 16 consecutive block pixels (row boundaries ignored)
     const int rp4 = rp / 4;
 
     auto issue = [&](int ch, int st) {
         float* xs = psm + st * STAGE;
         float* ws = xs + kPK * kPF;
-        const int qi = ch / segs, sg = ch - qi * segs;
-        const int qj0 = sg * kPK;
-        const int kc = min(kPK, bw - qj0);
-        const int64_t pix0 = (int64_t)(i0 + qi) * d2 + j0 + qj0;
+        const int q0 = ch * kPK;
+        const int kc = min(kPK, bpix - q0);
         for (int idx = tid; idx < kc * (kPF / 4); idx += NT) {
             const int k = idx / (kPF / 4), c4 = idx - k * (kPF / 4);
+            const int q = q0 + k;
+            const int qi = q / bw, qj = q - qi * bw;
+            const int64_t pix = (int64_t)(i0 + qi) * d2 + j0 + qj;
             const int64_t f = f0 + 4 * c4;
             float* dst = xs + k * kPF + 4 * c4;
-            if (f < ld) cp_async16(dst, mv + (pix0 + k) * ld + f);
+            if (f < ld) cp_async16(dst, mv + pix * ld + f);
             else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const int q0 = qi * bw + qj0;
         for (int idx = tid; idx < kc * (NC / 4); idx += NT) {
             const int k = idx / (NC / 4), c4 = idx - k * (NC / 4);
             float* dst = ws + k * NC + 4 * c4;
@@ -158,8 +204,7 @@ block_project_t_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld, 
         cp_async_commit();
         const float* xs = psm + (ch % kPStages) * STAGE;
         const float* ws = xs + kPK * kPF;
-        const int sg = ch % segs;
-        const int kc = min(kPK, bw - sg * kPK);
+        const int kc = min(kPK, bpix - ch * kPK);
 #pragma unroll 4
         for (int k = 0; k < kc; ++k) {
             const float4 xa = *reinterpret_cast<const float4*>(xs + k * kPF + 4 * lane);
@@ -334,6 +379,22 @@ extern "C" int pmd_block_pool_tavg(const float* yt, int64_t ld, int64_t t, int64
     dim3 grid((unsigned)((tp + 127) / 128), (unsigned)nb);
     pmd::block_pool_tavg_t_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(yt, ld, t, d2, starts, (int)bh, (int)bw, (int)saf,
                                                                          (int)taf, bta);
+    return pmd::check_launch(fn);
+}
+
+extern "C" int pmd_block_pool_full(const float* yt, int64_t ld, int64_t t, int64_t d2, const int32_t* starts, int64_t nb,
+                                   int64_t bh, int64_t bw, int64_t saf, int64_t taf, float* pooled, float* bta, void* stream) {
+    const char* fn = "pmd_block_pool_full";
+    PMD_REQUIRE(yt && starts && pooled && bta, fn, "null pointer");
+    PMD_REQUIRE(t > 0 && ld >= t && nb > 0 && nb <= 65535 && bh > 0 && bw > 0 && saf > 0 && taf > 0 && t % taf == 0, fn,
+                "bad size (t a multiple of taf)");
+    const int64_t P = ((bh + saf - 1) / saf) * ((bw + saf - 1) / saf);
+    const int64_t tp = t / taf;
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid((unsigned)((ld + 255) / 256), (unsigned)nb);
+    pmd::block_pool_full_kernel<<<grid, 256, 0, st>>>(yt, ld, t, d2, starts, (int)bh, (int)bw, (int)saf, pooled);
+    const int64_t total = nb * P * tp;
+    pmd::block_tavg_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pooled, ld, nb * P, tp, (int)taf, bta);
     return pmd::check_launch(fn);
 }
 

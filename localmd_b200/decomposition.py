@@ -251,7 +251,13 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
     d, ld = yt.shape
     nb = starts_dev.shape[0]
     rp = (r + 3) // 4 * 4
-    bta = ops.block_pool_tavg(yt, t, d2, starts_dev, bh, bw, saf, taf)  # (nb, P, t') = B_ta
+    ph, pw = -(-bh // saf), -(-bw // saf)
+    pooled = None
+    if nb * ph * pw * ld * 4 <= 24 << 30:
+        # B_ds at full time resolution is kept (5.2 GB at C2) so that U_ds^T B_ds contracts over the pooled pixels
+        pooled, bta = ops.block_pool_full(yt, t, d2, starts_dev, bh, bw, saf, taf)  # (nb, P, ld), (nb, P, t')
+    else:
+        bta = ops.block_pool_tavg(yt, t, d2, starts_dev, bh, bw, saf, taf)  # (nb, P, t') = B_ta
     _submark("blocks.pool")
     P = bta.shape[1]
     l = sketches.shape[2]
@@ -270,9 +276,16 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
         uds = e[:, :, :r].contiguous()
     del bta
     _submark("blocks.rsvd")
-    w4 = ops.block_unpool(uds, bh, bw, saf, rp)  # (nb, b, rp)
-    vds = ops.block_project(yt, 0, ld, d2, starts_dev, bh, bw, w4, r)  # (nb, r, ld)
-    del w4
+    if pooled is not None:
+        udp = torch.zeros((nb, ph * pw, rp), dtype=torch.float32, device=dev)
+        udp[:, :, :r] = uds
+        zero_starts = torch.zeros((nb, 2), dtype=torch.int32, device=dev)
+        vds = ops.block_project(pooled, ph * pw * ld, ld, pw, zero_starts, ph, pw, udp, r)  # (nb, r, ld) = U_ds^T B_ds
+        del pooled, udp
+    else:
+        w4 = ops.block_unpool(uds, bh, bw, saf, rp)  # (nb, b, rp): w4^T B == U_ds^T B_ds
+        vds = ops.block_project(yt, 0, ld, d2, starts_dev, bh, bw, w4, r)  # (nb, r, ld)
+        del w4
     _submark("blocks.project1")
     g4 = ops.gram_rows(vds)  # (nb, r, r) float64: V_ds V_ds^T
     _submark("blocks.gram1")

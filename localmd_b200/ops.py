@@ -23,7 +23,7 @@ NUMPY_NATIVE = {np.dtype(k): v for k, v in [("float32", torch.float32), ("uint16
                                                ("uint8", torch.uint8), ("float64", torch.float64), ("int32", torch.int32)]}
 
 LAUNCHES = {"count": 0, "by_name": {}}  # number of libpmd kernel launches issued (bench.py reports it)
-_KERNELS_PER_CALL = {"pmd_block_stats_rank": 3}
+_KERNELS_PER_CALL = {"pmd_block_stats_rank": 3, "pmd_block_pool_full": 2}
 
 
 def _count(name, n=None):
@@ -220,6 +220,18 @@ def block_pool_tavg(yt, t, d2, starts, bh, bw, saf, taf):
     bta = torch.empty((nb, ph * pw, t // taf), dtype=torch.float32, device=yt.device)
     _call("pmd_block_pool_tavg", _p(yt), ld, t, d2, _p(starts), nb, bh, bw, saf, taf, _p(bta), _stream())
     return bta
+
+
+def block_pool_full(yt, t, d2, starts, bh, bw, saf, taf):
+    """(pooled (nb, P, ld) full time resolution, bta (nb, P, t // taf)) of the pixel-major init movie yt (d, ld)."""
+    _req(yt, torch.float32, "yt"), _req(starts, torch.int32, "starts")
+    d, ld = yt.shape
+    nb = starts.shape[0]
+    ph, pw = -(-bh // saf), -(-bw // saf)
+    pooled = torch.empty((nb, ph * pw, ld), dtype=torch.float32, device=yt.device)
+    bta = torch.empty((nb, ph * pw, t // taf), dtype=torch.float32, device=yt.device)
+    _call("pmd_block_pool_full", _p(yt), ld, t, d2, _p(starts), nb, bh, bw, saf, taf, _p(pooled), _p(bta), _stream())
+    return pooled, bta
 
 
 def block_unpool(uds, bh, bw, saf, rp):

@@ -58,10 +58,8 @@ class PMDArray:
 
     @staticmethod
     def _to_host(t):
-        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-        buf.copy_(t, non_blocking=True)
-        torch.cuda.current_stream(t.device).synchronize()
-        return buf.numpy()
+        # one-off copies: page-locking a fresh buffer costs more than the driver's staged pageable copy
+        return t.cpu().numpy()
 
     def _materialise(self, what):
         lz = self._lazy

@@ -190,6 +190,9 @@ def test_block_pool_tavg_and_unpool(ops, bh, bw, saf, taf):
     t, d1, d2 = 120, 33, 41
     y, starts = _block_setup(rng, t, d1, d2, bh, bw)
     bta = ops.block_pool_tavg(dev(_pixel_major(y)), t, d2, dev(starts), bh, bw, saf, taf).cpu().numpy()
+    pooled, bta2 = ops.block_pool_full(dev(_pixel_major(y)), t, d2, dev(starts), bh, bw, saf, taf)
+    assert torch.equal(bta2.cpu(), torch.from_numpy(bta))  # same arithmetic, same order
+    pooled = pooled.cpu().numpy()
     r = 3
     ph, pw = -(-bh // saf), -(-bw // saf)
     uds = rng.standard_normal((len(starts), ph * pw, r)).astype(np.float32)
@@ -199,6 +202,8 @@ def test_block_pool_tavg_and_unpool(ops, bh, bw, saf, taf):
         ds = O.downsample_average_pooling(block, saf)
         ta = ds.reshape(ph * pw, t // taf, taf).mean(axis=2)  # C-order pooled pixel index, consecutive frame bins
         np.testing.assert_allclose(bta[b], ta, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(pooled[b][:, :t], ds.reshape(ph * pw, t), rtol=1e-6, atol=1e-6)
+        assert np.all(pooled[b][:, t:] == 0)
         lhs = w4[b][:, :r].T.astype(np.float64) @ block.reshape(bh * bw, t).astype(np.float64)
         rhs = uds[b].T.astype(np.float64) @ ds.reshape(ph * pw, t).astype(np.float64)
         np.testing.assert_allclose(lhs, rhs, atol=1e-4)

@@ -117,6 +117,13 @@ int pmd_block_project(const float* movie_t, int64_t movie_batch_stride, int64_t 
                       const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* w, int64_t r,
                       int64_t rp, float* out, int64_t ldo, void* stream);
 
+/* the same block projection on the tcgen05 tensor cores (3xTF32, float32-class accuracy, accumulators in tensor
+ * memory).  w_hi / w_lo: [nb][bh*bw][rp] float32 with w = w_hi + w_lo and w_hi exactly representable in TF32 (low 13
+ * mantissa bits zero); rp <= 64.  Same outputs as pmd_block_project. */
+int pmd_block_project_tc(const float* movie_t, int64_t movie_batch_stride, int64_t ld, int64_t d2,
+                         const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* w_hi,
+                         const float* w_lo, int64_t r, int64_t rp, float* out, int64_t ldo, void* stream);
+
 /* streaming spatial projection  s[b][q][c] = sum_f Y_b[q][f] * v[b][c][f]   (all ldv frames of v).
  * replaces: decomposition.py:304-306 (block * v_basis^T).   v: [nb][r][ldv] (ldv multiple of 4, padding
  * zero); s: [nb][bh*bw][rp], rp <= 64. */

@@ -228,7 +228,7 @@ def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, 
         rp = (l + 3) // 4 * 4
         qp = torch.zeros((m, b, rp), dtype=torch.float32, device=device)
         qp[:, :, :l] = q
-        bq = ops.block_project(noise, b * ld, ld, bw, starts[:m], bh, bw, qp, l)  # (m, l, ld)
+        bq = ops.block_project_tc(noise, b * ld, ld, bw, starts[:m], bh, bw, qp, l)  # (m, l, ld)
         _, e = ops.jacobi_eigh(ops.gram_rows(bq), mode=0)
         e1 = e[:, :, :1].contiguous()  # (m, l, 1)
         u1 = torch.zeros((m, b, 4), dtype=torch.float32, device=device)
@@ -280,11 +280,11 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
         udp = torch.zeros((nb, ph * pw, rp), dtype=torch.float32, device=dev)
         udp[:, :, :r] = uds
         zero_starts = torch.zeros((nb, 2), dtype=torch.int32, device=dev)
-        vds = ops.block_project(pooled, ph * pw * ld, ld, pw, zero_starts, ph, pw, udp, r)  # (nb, r, ld) = U_ds^T B_ds
+        vds = ops.block_project_tc(pooled, ph * pw * ld, ld, pw, zero_starts, ph, pw, udp, r)  # (nb, r, ld) = U_ds^T B_ds
         del pooled, udp
     else:
         w4 = ops.block_unpool(uds, bh, bw, saf, rp)  # (nb, b, rp): w4^T B == U_ds^T B_ds
-        vds = ops.block_project(yt, 0, ld, d2, starts_dev, bh, bw, w4, r)  # (nb, r, ld)
+        vds = ops.block_project_tc(yt, 0, ld, d2, starts_dev, bh, bw, w4, r)  # (nb, r, ld)
         del w4
     _submark("blocks.project1")
     g4 = ops.gram_rows(vds)  # (nb, r, r) float64: V_ds V_ds^T
@@ -304,7 +304,7 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
         uf = ops.orthonormalize_cols(torch.bmm(s_raw, tpad), r)
     del s_raw
     _submark("blocks.orth_s")
-    vn = ops.block_project(yt, 0, ld, d2, starts_dev, bh, bw, uf, r)  # (nb, r, ld)
+    vn = ops.block_project_tc(yt, 0, ld, d2, starts_dev, bh, bw, uf, r)  # (nb, r, ld): tcgen05, 3xTF32
     _submark("blocks.project2")
     g6 = ops.gram_rows(vn)
     _submark("blocks.gram2")

@@ -259,6 +259,23 @@ def block_project(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, w, r, ldo
     return out
 
 
+def block_project_tc(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, w, r, ldo=None):
+    """block_project on the tcgen05 tensor cores (3xTF32 with float32 accumulation in tensor memory); rp <= 64."""
+    _req(movie_t, torch.float32, "movie_t"), _req(w, torch.float32, "w"), _req(starts, torch.int32, "starts")
+    nb, bpix, rp = w.shape
+    assert bpix == bh * bw and starts.shape[0] == nb and rp <= 64
+    ldo = ld if ldo is None else int(ldo)
+    w_hi, w_lo = _split_tf32(w)
+    out = torch.empty((nb, r, ldo), dtype=torch.float32, device=movie_t.device)
+    step = 65535
+    for s in range(0, nb, step):
+        m = min(step, nb - s)
+        mv = ctypes.c_void_p(movie_t.data_ptr() + 4 * s * movie_batch_stride)
+        _call("pmd_block_project_tc", mv, movie_batch_stride, ld, d2, _p(starts[s:]), m, bh, bw, _p(w_hi[s:]), _p(w_lo[s:]), r, rp,
+              _p(out[s:]), ldo, _stream())
+    return out
+
+
 def block_spatial(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, v, rp):
     """s[b, q, c] = sum_f Y_b[q, f] * v[b, c, f];  v (nb, r, ldv) with zero padding -> (nb, bh*bw, rp)."""
     _req(movie_t, torch.float32, "movie_t"), _req(v, torch.float32, "v"), _req(starts, torch.int32, "starts")

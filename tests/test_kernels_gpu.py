@@ -238,6 +238,29 @@ def test_block_project_and_spatial(ops, bh, bw, r, t):
         assert np.all(s[b][:, r:] == 0)
 
 
+@pytest.mark.parametrize("bh,bw,r,t", [(20, 20, 50, 300), (16, 16, 8, 130), (10, 12, 5, 64), (22, 22, 64, 515), (10, 10, 1, 30)])
+def test_block_project_tensor_core(ops, bh, bw, r, t):
+    """tcgen05 3xTF32 block projection against float64 (float32-class accuracy, not TF32 accuracy)."""
+    rng = np.random.default_rng(r + t)
+    d1, d2 = 47, 52
+    y, starts = _block_setup(rng, t, d1, d2, bh, bw)
+    y *= np.exp(rng.uniform(-3, 3, size=(1, d1, d2))).astype(np.float32)  # wide dynamic range across pixels
+    nb = len(starts)
+    rp = (r + 3) // 4 * 4
+    w = np.zeros((nb, bh * bw, rp), np.float32)
+    w[:, :, :r] = rng.standard_normal((nb, bh * bw, r))
+    yt = _pixel_major(y)
+    ld = yt.shape[1]
+    out = ops.block_project_tc(dev(yt), 0, ld, d2, dev(starts), bh, bw, dev(w), r).cpu().numpy()
+    assert out.shape == (nb, r, ld)
+    for b, (i0, j0) in enumerate(starts):
+        blk = y[:, i0 : i0 + bh, j0 : j0 + bw].reshape(t, bh * bw).T.astype(np.float64)
+        ref = w[b][:, :r].T.astype(np.float64) @ blk
+        scale = np.abs(w[b][:, :r].T.astype(np.float64)) @ np.abs(blk)
+        assert np.max(np.abs(out[b][:, :t] - ref) / scale) < 3e-6
+        assert np.all(out[b][:, t:] == 0)
+
+
 def test_block_project_batched_movies(ops):
     """movie_batch_stride != 0: every 'block' is its own small pixel-major movie (threshold simulation)."""
     rng = np.random.default_rng(0)

@@ -68,9 +68,13 @@ int pmd_gram_f64(const float* a, int64_t batch, int64_t n, int64_t m_len, int64_
  *   0: orthonormal eigenvectors E
  *   1: E * diag(1/sqrt(w))  ("whitening": X*vecs has orthonormal columns when c = X^T X);
  *      columns with w_j <= w_0 * 1e-24 are zeroed
+ * sweeps_f32 != 0: the rotations run in float32 (reference-level accuracy, 1e-7 of the largest eigenvalue) -- used
+ * for the sketch-stage SVD of decomposition.py:66, whose result only seeds the temporal basis; the float64 CUDA-core
+ * rate of this GPU is ~1/64 of float32.
  * replaces: the small LAPACK SVD/eigh factorisations inside decomposition.py:66,301,315,319 and
  *           pmd_loader.py:60. */
-int pmd_jacobi_eigh(double* c, int64_t batch, int64_t n, int mode, double* w, float* vecs, void* stream);
+int pmd_jacobi_eigh(double* c, int64_t batch, int64_t n, int mode, int sweeps_f32, double* w, float* vecs,
+                    void* stream);
 
 /* gather + standardise + TRANSPOSE frames into the pixel-major init movie used by the block stage:
  *   out[p*ld + i] = (movie[frames[i]][p] - mean[p]) / stdv[p]   (i < n_frames; columns n_frames..ld-1 are zeroed)

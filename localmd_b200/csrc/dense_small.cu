@@ -106,17 +106,22 @@ gram_f64_kernel(const float* __restrict__ a, int n, int64_t m_len, int64_t bs, i
 // ------------------------------------------------------------------------------------------------
 constexpr int kJacThreads = 256;
 
+// S = working precision of the sweeps: double (default) or float (for sketch-stage subspaces, where the float64 CUDA-core
+// rate of this GPU -- about 1/64 of float32 -- would dominate the whole block stage).
+template <typename S>
 __global__ void __launch_bounds__(kJacThreads)
 jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, double* __restrict__ w_out,
                    float* __restrict__ vec_out) {
-    extern __shared__ double jsm[];
+    extern __shared__ __align__(16) unsigned char jsm_raw[];
+    S* jsm = reinterpret_cast<S*>(jsm_raw);
+    const S kTol = sizeof(S) == 8 ? (S)1e-15 : (S)3e-7;
     const int ld = n | 1;
     const int N = n + (n & 1);
     const int half = N / 2;
-    double* A = jsm;                 // [n][ld]
-    double* V = A + (size_t)n * ld;  // [n][ld]
-    double* cc = V + (size_t)n * ld; // [half]
-    double* ss = cc + half;          // [half]
+    S* A = jsm;                 // [n][ld]
+    S* V = A + (size_t)n * ld;  // [n][ld]
+    S* cc = V + (size_t)n * ld; // [half]
+    S* ss = cc + half;          // [half]
     int* pp = reinterpret_cast<int*>(ss + half);  // [half]
     int* qq = pp + half;                          // [half]
     __shared__ int n_rot;
@@ -126,8 +131,8 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
 
     for (int idx = tid; idx < n * n; idx += kJacThreads) {
         const int i = idx / n, j = idx % n;
-        A[i * ld + j] = cb[idx];
-        V[i * ld + j] = (i == j) ? 1.0 : 0.0;
+        A[i * ld + j] = (S)cb[idx];
+        V[i * ld + j] = (i == j) ? (S)1 : (S)0;
     }
     __syncthreads();
 
@@ -140,14 +145,14 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
                 if (tid == 0) { p = N - 1; q = step; }
                 else { p = (step + tid) % (N - 1); q = (step - tid + (N - 1)) % (N - 1); }
                 if (p > q) { const int tmp = p; p = q; q = tmp; }
-                double c = 1.0, s = 0.0;
+                S c = 1, s = 0;
                 bool rot = false;
                 if (q < n) {
-                    const double apq = A[p * ld + q], app = A[p * ld + p], aqq = A[q * ld + q];
-                    if (apq != 0.0 && fabs(apq) > 1e-15 * sqrt(fabs(app * aqq))) {
-                        const double tau = (aqq - app) / (2.0 * apq);
-                        const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                        c = 1.0 / sqrt(1.0 + t * t);
+                    const S apq = A[p * ld + q], app = A[p * ld + p], aqq = A[q * ld + q];
+                    if (apq != (S)0 && fabs(apq) > kTol * sqrt(fabs(app * aqq))) {
+                        const S tau = (aqq - app) / ((S)2 * apq);
+                        const S t = (tau >= (S)0 ? (S)1 : (S)-1) / (fabs(tau) + sqrt((S)1 + tau * tau));
+                        c = (S)1 / sqrt((S)1 + t * t);
                         s = t * c;
                         rot = true;
                     }
@@ -165,11 +170,11 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
                 const int p = pp[k];
                 if (p < 0) continue;
                 const int q = qq[k];
-                const double c = cc[k], s = ss[k];
-                const double aip = A[i * ld + p], aiq = A[i * ld + q];
+                const S c = cc[k], s = ss[k];
+                const S aip = A[i * ld + p], aiq = A[i * ld + q];
                 A[i * ld + p] = c * aip - s * aiq;
                 A[i * ld + q] = s * aip + c * aiq;
-                const double vip = V[i * ld + p], viq = V[i * ld + q];
+                const S vip = V[i * ld + p], viq = V[i * ld + q];
                 V[i * ld + p] = c * vip - s * viq;
                 V[i * ld + q] = s * vip + c * viq;
             }
@@ -180,8 +185,8 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
                 const int p = pp[k];
                 if (p < 0) continue;
                 const int q = qq[k];
-                const double c = cc[k], s = ss[k];
-                const double apj = A[p * ld + j], aqj = A[q * ld + j];
+                const S c = cc[k], s = ss[k];
+                const S apj = A[p * ld + j], aqj = A[q * ld + j];
                 A[p * ld + j] = c * apj - s * aqj;
                 A[q * ld + j] = s * apj + c * aqj;
             }
@@ -193,21 +198,19 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
     }
 
     // sort descending (rank by counting), write eigenvalues and (scaled) eigenvectors
-    double* wv = cc;  // reuse: need n entries -> use A's diagonal directly instead
-    (void)wv;
     double wmax = -1e300;
-    for (int i = 0; i < n; ++i) wmax = fmax(wmax, A[i * ld + i]);
+    for (int i = 0; i < n; ++i) wmax = fmax(wmax, (double)A[i * ld + i]);
     for (int idx = tid; idx < n * n; idx += kJacThreads) {
         const int r = idx / n, i = idx % n;  // element r of eigenvector i
-        const double wi = A[i * ld + i];
+        const double wi = (double)A[i * ld + i];
         int rank = 0;
         for (int j = 0; j < n; ++j) {
-            const double wj = A[j * ld + j];
+            const double wj = (double)A[j * ld + j];
             rank += (wj > wi) || (wj == wi && j < i);
         }
         double scale = 1.0;
         if (mode == 1) scale = (wi > wmax * 1e-24 && wi > 0.0) ? rsqrt(wi) : 0.0;
-        vec_out[b * (int64_t)n * n + (int64_t)r * n + rank] = (float)(V[r * ld + i] * scale);
+        vec_out[b * (int64_t)n * n + (int64_t)r * n + rank] = (float)((double)V[r * ld + i] * scale);
         if (r == 0) w_out[b * (int64_t)n + rank] = wi;
     }
 }
@@ -236,16 +239,27 @@ extern "C" int pmd_gram_f64(const float* a, int64_t batch, int64_t n, int64_t m_
     return pmd::check_launch(fn);
 }
 
-extern "C" int pmd_jacobi_eigh(double* c, int64_t batch, int64_t n, int mode, double* w, float* vecs, void* stream) {
+extern "C" int pmd_jacobi_eigh(double* c, int64_t batch, int64_t n, int mode, int sweeps_f32, double* w, float* vecs,
+                               void* stream) {
     const char* fn = "pmd_jacobi_eigh";
     PMD_REQUIRE(c && w && vecs, fn, "null pointer");
     PMD_REQUIRE(batch > 0 && n > 0 && n <= 112, fn, "bad size (n <= 112)");
     PMD_REQUIRE(mode == 0 || mode == 1, fn, "mode must be 0 or 1");
     const int ld = (int)n | 1;
     const int half = ((int)n + ((int)n & 1)) / 2;
-    const size_t smem = (size_t)2 * n * ld * sizeof(double) + (size_t)2 * half * sizeof(double) + (size_t)2 * half * sizeof(int);
-    cudaError_t e = cudaFuncSetAttribute(pmd::jacobi_eigh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
-    pmd::jacobi_eigh_kernel<<<(unsigned)batch, pmd::kJacThreads, smem, (cudaStream_t)stream>>>(c, (int)n, mode, 40, w, vecs);
+    const size_t es = sweeps_f32 ? sizeof(float) : sizeof(double);
+    const size_t smem = ((size_t)2 * n * ld * es + (size_t)2 * half * es + 15) / 16 * 16 + (size_t)2 * half * sizeof(int);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sweeps_f32) {
+        auto k = pmd::jacobi_eigh_kernel<float>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
+        k<<<(unsigned)batch, pmd::kJacThreads, smem, st>>>(c, (int)n, mode, 40, w, vecs);
+    } else {
+        auto k = pmd::jacobi_eigh_kernel<double>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
+        k<<<(unsigned)batch, pmd::kJacThreads, smem, st>>>(c, (int)n, mode, 40, w, vecs);
+    }
     return pmd::check_launch(fn);
 }

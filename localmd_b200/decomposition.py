@@ -265,7 +265,9 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
         y = torch.bmm(bta, sketches)  # (nb, P, l)
         q = ops.block_orth(y) if ops.block_orth_fits(P, l) else ops.orthonormalize_cols(y)
         bq = torch.bmm(q.transpose(1, 2), bta).contiguous()  # (nb, l, t')
-        _, e = ops.jacobi_eigh(ops.gram_rows(bq), mode=0)
+        # sketch-stage SVD (decomposition.py:66): float32 rotations on the float64 Gram, the accuracy of the reference's
+        # own float32 SVD; its output only seeds the temporal basis that the full-resolution steps below refine
+        _, e = ops.jacobi_eigh(ops.gram_rows(bq), mode=0, sweeps_f32=True)
         uds = torch.bmm(q, e[:, :, :r]).contiguous()  # (nb, P, r)
         del y, q, bq, e
     else:
@@ -287,21 +289,16 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
         vds = ops.block_project_tc(yt, 0, ld, d2, starts_dev, bh, bw, w4, r)  # (nb, r, ld)
         del w4
     _submark("blocks.project1")
-    g4 = ops.gram_rows(vds)  # (nb, r, r) float64: V_ds V_ds^T
-    _submark("blocks.gram1")
-    # S = B Vb^T with Vb = L^-1 V_ds an orthonormal basis of the row space of V_ds (G = L L^T), i.e.
-    # S = (B V_ds^T) L^-T: the r x t basis change is applied to the small b x r product inside pmd_block_orth,
-    # which then orthonormalises S (decomposition.py:301-315; only the spans matter downstream).
+    # S' = B V_ds^T has the same column space as the reference's S = B Vb^T (Vb = orthonormalised rows of V_ds,
+    # decomposition.py:301-306), and only that space is used downstream (Uf = orth(S), 315); the rows of V_ds are the
+    # nearly orthogonal sketch directions, so S' only needs the column scaling that CholQR's relative pivots apply anyway.
     s_raw = ops.block_spatial(yt, 0, ld, d2, starts_dev, bh, bw, vds, rp)  # (nb, b, rp)
     del vds
     _submark("blocks.spatial")
     if ops.block_orth_fits(bh * bw, r):
-        uf = ops.block_orth(s_raw, r, g_ext=g4)  # (nb, b, rp)
-    else:  # large blocks: eigen-whitening of the temporal basis + Gram/Jacobi orthonormalisation in global memory
-        _, tm = ops.jacobi_eigh(g4, mode=1)
-        tpad = torch.zeros((nb, rp, rp), dtype=torch.float32, device=dev)
-        tpad[:, :r, :r] = tm
-        uf = ops.orthonormalize_cols(torch.bmm(s_raw, tpad), r)
+        uf = ops.block_orth(s_raw, r)  # (nb, b, rp)
+    else:  # large blocks: Gram/Jacobi orthonormalisation in global memory
+        uf = ops.orthonormalize_cols(s_raw, r)
     del s_raw
     _submark("blocks.orth_s")
     vn = ops.block_project_tc(yt, 0, ld, d2, starts_dev, bh, bw, uf, r)  # (nb, r, ld): tcgen05, 3xTF32

@@ -116,13 +116,14 @@ def gram_f64(a, batch, n, m_len, batch_stride, row_stride, inner_stride):
     return c
 
 
-def jacobi_eigh(c, mode=0):
-    """c: (batch, n, n) float64 (destroyed).  Returns (w (batch,n) float64 descending, vecs (batch,n,n) float32)."""
+def jacobi_eigh(c, mode=0, sweeps_f32=False):
+    """c: (batch, n, n) float64 (destroyed).  Returns (w (batch,n) float64 descending, vecs (batch,n,n) float32).
+    sweeps_f32: run the Jacobi rotations in float32 (reference-level accuracy; ~10x faster on this GPU)."""
     _req(c, torch.float64, "c")
     batch, n, _ = c.shape
     w = torch.empty((batch, n), dtype=torch.float64, device=c.device)
     vecs = torch.empty((batch, n, n), dtype=torch.float32, device=c.device)
-    _call("pmd_jacobi_eigh", _p(c), batch, n, int(mode), _p(w), _p(vecs), _stream())
+    _call("pmd_jacobi_eigh", _p(c), batch, n, int(mode), int(bool(sweeps_f32)), _p(w), _p(vecs), _stream())
     return w, vecs
 
 

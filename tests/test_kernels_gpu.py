@@ -78,6 +78,15 @@ def test_gram_and_jacobi(ops, n, m, batch):
         assert np.abs(vecs[b].T @ vecs[b] - np.eye(n)).max() < 5e-6  # float32 storage of the vectors
         resid = ref[b] @ vecs[b] - vecs[b] * w[b][None, :]
         assert np.abs(resid).max() < 5e-6 * wr[0]
+    # float32 sweeps: eigenvalues to 1e-6 of the largest, an orthonormal basis, invariant subspaces of the top part
+    w32, v32 = ops.jacobi_eigh(g.clone(), mode=0, sweeps_f32=True)
+    w32, v32 = w32.cpu().numpy(), v32.cpu().numpy().astype(np.float64)
+    for b in range(batch):
+        wr = np.linalg.eigvalsh(ref[b])[::-1]
+        np.testing.assert_allclose(w32[b], wr, rtol=0, atol=1e-5 * wr[0])
+        assert np.abs(v32[b].T @ v32[b] - np.eye(n)).max() < 2e-5
+        resid = ref[b] @ v32[b] - v32[b] * w32[b][None, :]
+        assert np.abs(resid).max() < 2e-5 * wr[0]
     _, tm = ops.jacobi_eigh(g.clone(), mode=1)
     q = x.transpose(0, 2, 1).astype(np.float64) @ tm.cpu().numpy().astype(np.float64)
     for b in range(batch):

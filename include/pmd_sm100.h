@@ -135,6 +135,12 @@ int pmd_block_spatial(const float* movie_t, int64_t movie_batch_stride, int64_t 
                       const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* v, int64_t ldv,
                       int64_t r, int64_t rp, float* s, void* stream);
 
+/* the same spatial projection on the tcgen05 tensor cores (3xTF32, K-major SWIZZLE_128B operands, accumulators in
+ * tensor memory over the whole frame loop).  Same arguments and output as pmd_block_spatial. */
+int pmd_block_spatial_tc(const float* movie_t, int64_t movie_batch_stride, int64_t ld, int64_t d2,
+                         const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* v, int64_t ldv,
+                         int64_t r, int64_t rp, float* s, void* stream);
+
 /* roughness statistics of every component of every block + the keep-through-first-failure rule.
  * replaces: evaluation.py:84-126 (spatial/temporal_roughness_stat), 133-192, 195-222
  *           (filter_by_failures) and decomposition.py:502-506.

@@ -289,3 +289,220 @@ extern "C" int pmd_block_project_tc(const float* movie_t, int64_t movie_batch_st
         movie_t, movie_batch_stride, ld, d2, starts, (int)bh, (int)bw, w_hi, w_lo, (int)r, (int)rp, out, ldo);
     return pmd::check_launch(fn);
 }
+
+// =================================================================================================
+// Block spatial projection on tcgen05 (3xTF32):  s[b][q][c] = sum_f yT[pix(b,q)][f] * v[b][c][f]
+// (decomposition.py:304-306).  Per (block, 256-pixel tile) D[2 x 128 pixels][64 comps] = A[pixels x frames] B[frames x comps]:
+// both operands are K-major here (frames are contiguous for a pixel of yT and for a component of v), the canonical
+// SWIZZLE_128B layout: one 128-byte row (32 frames) per pixel / component, atoms of 8 rows, the 16-byte chunk index
+// XORed with the row index.  Producers (8 warps) copy A and B with 16-byte cp.async and split BOTH into hi / lo in
+// shared memory; one thread issues the MMAs (per 32-frame stage: 4 K steps x 2 pixel tiles x 3 products); the 128
+// accumulator columns live in tensor memory for the whole K loop (all frames).
+// =================================================================================================
+namespace pmd {
+
+constexpr int kSTTiles = 2;                         // 128-pixel accumulator tiles per CTA
+constexpr int kSTK = 32;                            // frames per stage (one 128-byte swizzle row)
+constexpr int kSTStages = 2;
+constexpr int kSTProducers = 256;
+constexpr int kSTABytes = 128 * 128;                // one A tile part (128 pixels x 32 frames)
+constexpr int kSTBBytes = 64 * 128;                 // one B part (64 comps x 32 frames)
+constexpr int kSTStageBytes = 2 * kSTTiles * kSTABytes + 2 * kSTBBytes;   // 80 KB
+
+// K-major SWIZZLE_128B descriptor (rows of 128 bytes, 8-row atoms 1024 bytes apart)
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(1024 >> 4) << 32;                          // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;                                    // descriptor version
+    d |= (uint64_t)2 << 61;                                    // SWIZZLE_128B
+    return d;
+}
+
+__global__ void __launch_bounds__(kSTProducers + 32, 1)
+block_spatial_tc_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld, int64_t d2, const int32_t* __restrict__ starts,
+                        int bh, int bw, const float* __restrict__ v, int64_t ldv, int r, int rp, float* __restrict__ s) {
+    extern __shared__ __align__(1024) unsigned char stsm[];
+    __shared__ __align__(8) uint64_t bar_full[kSTStages], bar_empty[kSTStages];
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t sbase = (smem_u32(stsm) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int64_t b = blockIdx.y;
+    const int q0 = blockIdx.x * (128 * kSTTiles);
+    const int i0 = starts[2 * b], j0 = starts[2 * b + 1];
+    const float* mv = movT + b * mbs;
+    const float* vb = v + b * (int64_t)r * ldv;
+    const int bpix = bh * bw;
+    const int nch = (int)((ldv + kSTK - 1) / kSTK);
+    constexpr uint32_t kCols = 64 * kSTTiles;
+
+    if (tid == 0) {
+        for (int st = 0; st < kSTStages; ++st) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(&bar_full[st])), "r"(kSTProducers));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_empty[st])));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(kCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+    const uint32_t tmem_d = tmem_base_s;
+    // D f32, A/B tf32, both K-major, N = 64, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+    if (warp < 8) {
+        // ================================ producers ================================
+        // A pieces: id = tid + 256 j (j < 8): 16-byte frame chunk c = id % 8, row = id / 8 (tile = row / 128, m = row % 128)
+        // B pieces: id = tid + 256 j (j < 2): chunk c = id % 8, component n = id / 8
+        const int c = tid & 7;
+        const float* pa[8];
+        uint32_t aoff[8];
+        bool a_ok[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int row = (tid >> 3) + 32 * j;
+            const int tile = row >> 7, m = row & 127;
+            const int q = q0 + row;
+            a_ok[j] = q < bpix;
+            const int qq = a_ok[j] ? q : 0;
+            const int qi = qq / bw, qj = qq - qi * bw;
+            pa[j] = mv + ((int64_t)(i0 + qi) * d2 + j0 + qj) * ld + 4 * c;
+            aoff[j] = tile * (2 * kSTABytes) + (m >> 3) * 1024 + (m & 7) * 128 + ((c ^ (m & 7)) << 4);
+        }
+        const float* pb[2];
+        uint32_t boff[2];
+        bool b_ok[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int n = (tid >> 3) + 32 * j;
+            b_ok[j] = n < r;
+            pb[j] = vb + (int64_t)(b_ok[j] ? n : 0) * ldv + 4 * c;
+            boff[j] = 2 * kSTTiles * kSTABytes + (n >> 3) * 1024 + (n & 7) * 128 + ((c ^ (n & 7)) << 4);
+        }
+        int fcur = 0;   // first frame of the next chunk to issue
+        auto issue = [&](int st) {
+            const uint32_t base = sbase + st * kSTStageBytes;
+            const bool f_ok = fcur + 4 * c < ldv;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (a_ok[j] && f_ok) tc_cp_async16(base + aoff[j], pa[j] + fcur);
+                else asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n" ::"r"(base + aoff[j]), "f"(0.f));
+            }
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                if (b_ok[j] && f_ok) tc_cp_async16(base + boff[j], pb[j] + fcur);
+                else asm volatile("st.shared.v4.f32 [%0], {%1, %1, %1, %1};\n" ::"r"(base + boff[j]), "f"(0.f));
+            }
+            fcur += kSTK;
+        };
+        auto split_piece = [&](uint32_t hi, uint32_t lo) {
+            float x0, x1, x2, x3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(hi));
+            const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+            const float h2 = __uint_as_float(__float_as_uint(x2) & 0xFFFFE000u), h3 = __uint_as_float(__float_as_uint(x3) & 0xFFFFE000u);
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(hi), "f"(h0), "f"(h1), "f"(h2), "f"(h3));
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(lo), "f"(x0 - h0), "f"(x1 - h1), "f"(x2 - h2), "f"(x3 - h3));
+        };
+        auto split = [&](int st) {
+            const uint32_t base = sbase + st * kSTStageBytes;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) split_piece(base + aoff[j], base + aoff[j] + kSTABytes);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) split_piece(base + boff[j], base + boff[j] + kSTBBytes);
+        };
+
+        issue(0);
+        asm volatile("cp.async.commit_group;\n" ::);
+        for (int ch = 0; ch < nch; ++ch) {
+            const int st = ch & 1;
+            if (ch + 1 < nch) {
+                if (ch >= 1) mbar_wait(smem_u32(&bar_empty[st ^ 1]), ((ch - 1) >> 1) & 1);
+                issue(st ^ 1);
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+            asm volatile("cp.async.wait_group 1;\n" ::);
+            split(st);
+            asm volatile("fence.proxy.async.shared::cta;\n" ::);
+            mbar_arrive(smem_u32(&bar_full[st]));
+        }
+        // ================================ epilogue ================================
+        mbar_wait(smem_u32(&bar_empty[(nch - 1) & 1]), ((nch - 1) >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+        const int tile = warp >> 2, quarter = warp & 3;       // a warp reads the TMEM lanes 32 (warp % 4) .. +31
+        const int q = q0 + 128 * tile + 32 * quarter + lane;
+#pragma unroll
+        for (int cq = 0; cq < 4; ++cq) {
+            if (16 * cq >= rp) break;
+            uint32_t vv[16];
+            const uint32_t taddr = tmem_d + ((uint32_t)(32 * quarter) << 16) + 64 * tile + 16 * cq;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                : "=r"(vv[0]), "=r"(vv[1]), "=r"(vv[2]), "=r"(vv[3]), "=r"(vv[4]), "=r"(vv[5]), "=r"(vv[6]), "=r"(vv[7]), "=r"(vv[8]),
+                  "=r"(vv[9]), "=r"(vv[10]), "=r"(vv[11]), "=r"(vv[12]), "=r"(vv[13]), "=r"(vv[14]), "=r"(vv[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            if (q < bpix) {
+                float* o = s + ((int64_t)b * bpix + q) * rp + 16 * cq;
+#pragma unroll
+                for (int i = 0; i < 16; i += 4) {
+                    if (16 * cq + i < rp)
+                        *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(vv[i]), __uint_as_float(vv[i + 1]),
+                                                                        __uint_as_float(vv[i + 2]), __uint_as_float(vv[i + 3]));
+                }
+            }
+        }
+    } else if (lane == 0) {
+        // ================================ MMA issuer ================================
+        for (int ch = 0; ch < nch; ++ch) {
+            const int st = ch & 1;
+            mbar_wait(smem_u32(&bar_full[st]), (ch >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+            const uint32_t base = sbase + st * kSTStageBytes;
+            const uint32_t b_hi = base + 2 * kSTTiles * kSTABytes, b_lo = b_hi + kSTBBytes;
+#pragma unroll
+            for (int ks = 0; ks < kSTK / 8; ++ks) {
+                const uint64_t dbh = umma_desc_k(b_hi + 32 * ks), dbl = umma_desc_k(b_lo + 32 * ks);
+#pragma unroll
+                for (int tl = 0; tl < kSTTiles; ++tl) {
+                    const uint32_t a_hi = base + tl * 2 * kSTABytes, a_lo = a_hi + kSTABytes;
+                    const uint64_t dah = umma_desc_k(a_hi + 32 * ks), dal = umma_desc_k(a_lo + 32 * ks);
+                    umma_tf32(tmem_d + 64 * tl, dah, dbl, idesc, (ch | ks) != 0);
+                    umma_tf32(tmem_d + 64 * tl, dal, dbh, idesc, 1u);
+                    umma_tf32(tmem_d + 64 * tl, dah, dbh, idesc, 1u);
+                }
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar_empty[st]))
+                         : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_d), "r"(kCols));
+}
+
+}  // namespace pmd
+
+extern "C" int pmd_block_spatial_tc(const float* movie_t, int64_t movie_batch_stride, int64_t ld, int64_t d2,
+                                    const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* v, int64_t ldv,
+                                    int64_t r, int64_t rp, float* s, void* stream) {
+    const char* fn = "pmd_block_spatial_tc";
+    PMD_REQUIRE(movie_t && starts && v && s, fn, "null pointer");
+    PMD_REQUIRE(ld > 0 && ld % 4 == 0 && ldv > 0 && ldv % 4 == 0 && ldv <= ld && nb > 0 && nb <= 65535 && r > 0 && rp >= r &&
+                    rp % 4 == 0 && rp <= 64,
+                fn, "bad size (ld, ldv multiples of 4, ldv <= ld, rp multiple of 4, r <= rp <= 64)");
+    PMD_REQUIRE(((uintptr_t)movie_t % 16) == 0 && ((uintptr_t)v % 16) == 0 && ((uintptr_t)s % 16) == 0 &&
+                    (movie_batch_stride % 4) == 0,
+                fn, "operands must be 16-byte aligned");
+    const size_t smem = pmd::kSTStages * pmd::kSTStageBytes + 1024;
+    cudaError_t e = cudaFuncSetAttribute(pmd::block_spatial_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
+    const int64_t bpix = bh * bw;
+    dim3 grid((unsigned)((bpix + 128 * pmd::kSTTiles - 1) / (128 * pmd::kSTTiles)), (unsigned)nb);
+    pmd::block_spatial_tc_kernel<<<grid, pmd::kSTProducers + 32, smem, (cudaStream_t)stream>>>(
+        movie_t, movie_batch_stride, ld, d2, starts, (int)bh, (int)bw, v, ldv, (int)r, (int)rp, s);
+    return pmd::check_launch(fn);
+}

@@ -292,7 +292,7 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
     # S' = B V_ds^T has the same column space as the reference's S = B Vb^T (Vb = orthonormalised rows of V_ds,
     # decomposition.py:301-306), and only that space is used downstream (Uf = orth(S), 315); the rows of V_ds are the
     # nearly orthogonal sketch directions, so S' only needs the column scaling that CholQR's relative pivots apply anyway.
-    s_raw = ops.block_spatial(yt, 0, ld, d2, starts_dev, bh, bw, vds, rp)  # (nb, b, rp)
+    s_raw = ops.block_spatial_tc(yt, 0, ld, d2, starts_dev, bh, bw, vds, rp)  # (nb, b, rp): tcgen05, 3xTF32
     del vds
     _submark("blocks.spatial")
     if ops.block_orth_fits(bh * bw, r):

@@ -291,6 +291,20 @@ def block_spatial(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, v, rp):
     return s_out
 
 
+def block_spatial_tc(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, v, rp):
+    """block_spatial on the tcgen05 tensor cores (3xTF32, float32 accumulation in tensor memory); rp <= 64."""
+    _req(movie_t, torch.float32, "movie_t"), _req(v, torch.float32, "v"), _req(starts, torch.int32, "starts")
+    nb, r, ldv = v.shape
+    s_out = torch.empty((nb, bh * bw, rp), dtype=torch.float32, device=movie_t.device)
+    step = 65535
+    for s in range(0, nb, step):
+        m = min(step, nb - s)
+        mv = ctypes.c_void_p(movie_t.data_ptr() + 4 * s * movie_batch_stride)
+        _call("pmd_block_spatial_tc", mv, movie_batch_stride, ld, d2, _p(starts[s:]), m, bh, bw, _p(v[s:]), ldv, r, rp,
+              _p(s_out[s:]), _stream())
+    return s_out
+
+
 def block_stats_rank(u, v, bh, bw, r, thr_s, thr_t, max_fail, t=None):
     """v: (nb, r, ldv); the temporal statistic uses the first t columns of every row (default: all)."""
     _req(u, torch.float32, "u"), _req(v, torch.float32, "v")

@@ -25,3 +25,7 @@ def timeit(name, fn, reps=3):
 a = timeit("block_project (SIMT)", lambda: ops.block_project(yt, 0, t, d2, starts, bh, bw, w, r))
 b = timeit("block_project_tc", lambda: ops.block_project_tc(yt, 0, t, d2, starts, bh, bw, w, r))
 print("max |tc - simt| / max|simt| = %.2e" % ((a - b).abs().max() / a.abs().max()).item())
+vb = torch.randn((nb, r, t), device=dev)
+c = timeit("block_spatial (SIMT)", lambda: ops.block_spatial(yt, 0, t, d2, starts, bh, bw, vb, rp))
+d = timeit("block_spatial_tc", lambda: ops.block_spatial_tc(yt, 0, t, d2, starts, bh, bw, vb, rp))
+print("max |tc - simt| / max|simt| = %.2e" % ((c - d).abs().max() / c.abs().max()).item())

@@ -270,6 +270,28 @@ def test_block_project_tensor_core(ops, bh, bw, r, t):
         assert np.all(out[b][:, t:] == 0)
 
 
+@pytest.mark.parametrize("bh,bw,r,t", [(20, 20, 50, 300), (16, 16, 8, 130), (10, 12, 5, 64), (22, 22, 64, 515), (32, 32, 50, 259)])
+def test_block_spatial_tensor_core(ops, bh, bw, r, t):
+    """tcgen05 3xTF32 spatial projection against float64."""
+    rng = np.random.default_rng(r + t)
+    d1, d2 = 47, 52
+    y, starts = _block_setup(rng, t, d1, d2, bh, bw)
+    y *= np.exp(rng.uniform(-3, 3, size=(1, d1, d2))).astype(np.float32)
+    nb = len(starts)
+    rp = (r + 3) // 4 * 4
+    yt = _pixel_major(y)
+    ld = yt.shape[1]
+    vb = np.zeros((nb, r, ld), np.float32)
+    vb[:, :, :t] = rng.standard_normal((nb, r, t)) * np.exp(rng.uniform(-2, 2, size=(nb, r, 1)))
+    s = ops.block_spatial_tc(dev(yt), 0, ld, d2, dev(starts), bh, bw, dev(vb), rp).cpu().numpy()
+    for b, (i0, j0) in enumerate(starts):
+        blk = y[:, i0 : i0 + bh, j0 : j0 + bw].reshape(t, bh * bw).T.astype(np.float64)  # (b, t)
+        ref = blk @ vb[b][:, :t].T.astype(np.float64)
+        scale = np.abs(blk) @ np.abs(vb[b][:, :t].T.astype(np.float64))
+        assert np.max(np.abs(s[b][:, :r] - ref) / scale) < 3e-6
+        assert np.all(s[b][:, r:] == 0)
+
+
 def test_block_project_batched_movies(ops):
     """movie_batch_stride != 0: every 'block' is its own small pixel-major movie (threshold simulation)."""
     rng = np.random.default_rng(0)

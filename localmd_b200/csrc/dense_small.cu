@@ -165,30 +165,33 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
             }
             __syncthreads();
             // column rotations of A and V:  col_p <- c col_p - s col_q,  col_q <- s col_p + c col_q
-            for (int item = tid; item < half * n; item += kJacThreads) {
-                const int k = item / n, i = item % n;
+            // (thread = pair slot tid / 8, rows tid % 8, +8, ...: no integer divisions in the hot loop)
+            for (int k = tid >> 3; k < half; k += kJacThreads >> 3) {
                 const int p = pp[k];
                 if (p < 0) continue;
                 const int q = qq[k];
                 const S c = cc[k], s = ss[k];
-                const S aip = A[i * ld + p], aiq = A[i * ld + q];
-                A[i * ld + p] = c * aip - s * aiq;
-                A[i * ld + q] = s * aip + c * aiq;
-                const S vip = V[i * ld + p], viq = V[i * ld + q];
-                V[i * ld + p] = c * vip - s * viq;
-                V[i * ld + q] = s * vip + c * viq;
+                for (int i = tid & 7; i < n; i += 8) {
+                    const S aip = A[i * ld + p], aiq = A[i * ld + q];
+                    A[i * ld + p] = c * aip - s * aiq;
+                    A[i * ld + q] = s * aip + c * aiq;
+                    const S vip = V[i * ld + p], viq = V[i * ld + q];
+                    V[i * ld + p] = c * vip - s * viq;
+                    V[i * ld + q] = s * vip + c * viq;
+                }
             }
             __syncthreads();
             // row rotations of A
-            for (int item = tid; item < half * n; item += kJacThreads) {
-                const int k = item / n, j = item % n;
+            for (int k = tid >> 3; k < half; k += kJacThreads >> 3) {
                 const int p = pp[k];
                 if (p < 0) continue;
                 const int q = qq[k];
                 const S c = cc[k], s = ss[k];
-                const S apj = A[p * ld + j], aqj = A[q * ld + j];
-                A[p * ld + j] = c * apj - s * aqj;
-                A[q * ld + j] = s * apj + c * aqj;
+                for (int j = tid & 7; j < n; j += 8) {
+                    const S apj = A[p * ld + j], aqj = A[q * ld + j];
+                    A[p * ld + j] = c * apj - s * aqj;
+                    A[q * ld + j] = s * apj + c * aqj;
+                }
             }
             __syncthreads();
         }

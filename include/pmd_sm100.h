@@ -215,6 +215,44 @@ int pmd_make_strips(const int32_t* row_starts, int64_t nbr, const int32_t* col_s
                     int32_t* tasks_out, int64_t cap_tasks, int64_t* local8_out, int64_t* local4_out,
                     int64_t* counts);
 
+/* K7 on the tensor cores (tcgen05, sm_100a): the same projection as pmd_project_stream, computed as
+ *   D[128 frames x 128 slot columns] += A[128 frames x 32 pixels] * B[32 pixels x 128 slot columns]
+ * per strip row, 32-pixel chunk and 128-frame tile, float32-accurate by a TF32 main product plus one bf16 MMA for
+ * both correction terms; accumulators in tensor memory (4 frame tiles x 128 columns).  Needs d2 % 4 == 0 and a
+ * 16-byte aligned movie.  Tables come from pmd_make_strips_tc, the coefficient images from pmd_pack_strips_tc:
+ *   items:  [n_items][12] int32 = (first column c0 (multiple of 4), width / 8, first row, rows, first image chunk,
+ *           32-pixel chunks per row, first event, events, bg partial index, first slot_ptr entry, 0, 0)
+ *   events: [n][4] int32 = (row, slot, first output column, n comps | kind << 8), ascending per item: after that row
+ *           the slot is read and cleared; kind 0 stores finished local columns to z, kind 1 ADDS a partial sum of
+ *           background columns to zbg (zbg must be zero on entry)
+ *   bimg:   per (item, row, chunk) 32 KB: [128 columns][32 pixels] TF32 part + bf16 pair part, SWIZZLE_128B images
+ * Outputs as pmd_project_stream (z rows of local tasks written once; one background partial per strip in zbg).
+ * replaces: pmd_loader.py:316-346, 392-414 (v_projection / v_projection_routine) in full. */
+int pmd_project_stream_tc(const void* movie, int dtype, int64_t t, int64_t d2, int64_t d, const int32_t* items,
+                          int64_t n_items, const int32_t* events, const void* bimg, const float* mean,
+                          const float* inv_std, float* z, int64_t ldz, float* zbg, int64_t ldzbg, int64_t bg_stride,
+                          void* stream);
+
+/* HOST function (every pointer is a HOST pointer): tables of pmd_project_stream_tc.  Strips of G block columns
+ * (<= 128 pixels), 32 slots of 4 accumulator columns, tasks = (block, <= 4 components) or 4 background components;
+ * g_fixed > 0 forces G.  Outputs (caller allocated): items [cap_items][12], slot_ptr [cap_items*33], tasks
+ * [cap_tasks][8] = (first row, first column relative to c0, rows, width, first output column, n comps, kind, 0),
+ * events [cap_events][4], counts[8] = (n_items, n_tasks, n_events, image chunks, n_parts, max width / 8, G, 0);
+ * counts[0] == 0: geometry not supported.
+ * replaces: nothing in the reference (host bookkeeping of the new projection kernel). */
+int pmd_make_strips_tc(const int32_t* row_starts, int64_t nbr, const int32_t* col_starts, int64_t nbc, int64_t bh,
+                       int64_t bw, int64_t d1, int64_t d2, const int64_t* ranks, const int64_t* col0, int64_t n_bg,
+                       int64_t g_fixed, int32_t* items_out, int64_t cap_items, int32_t* slot_ptr_out,
+                       int32_t* tasks_out, int64_t cap_tasks, int32_t* events_out, int64_t cap_events, int64_t* counts);
+
+/* Builds the coefficient images of pmd_project_stream_tc on the device: one CTA per (item, row) pair listed in
+ * item_of_row [n_rows_total][2] = (item, row - first row of the item).  uvals: block-component values
+ * [column][bh*bw] float32, bg: [K][d] float32 dense background rows (may be NULL when there are none).
+ * replaces: nothing in the reference (operand packing of the new projection kernel). */
+int pmd_pack_strips_tc(const int32_t* items, const int32_t* item_of_row, int64_t n_rows_total, const int32_t* slot_ptr,
+                       const int32_t* tasks, const float* uvals, int64_t bpix, const float* bg, int64_t d, int64_t d2,
+                       void* bimg, void* stream);
+
 /* K7b  full-movie projection onto dense (background) columns:
  *   z[c][f] += sum_p basis[c][p] * (movie[f][p] - mean[p]) * inv_std[p]     (c < k <= 16)
  * replaces: the same v_projection for the dense background columns appended at

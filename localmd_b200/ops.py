@@ -731,3 +731,74 @@ def project_stream(movie2d, d2, st_dev, upack, mean, inv_std, z_local, z_bg):
           _p(st_dev["slot_ptr"]), _p(st_dev["tasks"]), st_dev["max_rw"], _p(upack), _p(mean), _p(inv_std), _p(zl),
           zl.stride(0) if z_local.numel() else t, _p(parts), t, K * t, _stream())
     z_bg[:, :t].copy_(parts.sum(dim=0))
+
+
+# ---- K7 on the tensor cores (csrc/project_tc.cu, strips_tc_host.cu) ----------------------------------------------
+TC_SLOTS, TC_CHUNK_BYTES = 32, 32768
+
+
+def make_strips_tc(row_starts, col_starts, bh, bw, d1, d2, ranks_host, col0_host, n_bg, G=None):
+    """Host tables for pmd_project_stream_tc (native routine pmd_make_strips_tc).  Returns a dict of numpy
+    tables, or None when the geometry is not supported by the tensor-core kernel (callers then use
+    make_strips / project_stream)."""
+    rs = np.ascontiguousarray(row_starts, dtype=np.int32)
+    cs = np.ascontiguousarray(col_starts, dtype=np.int32)
+    ranks = np.ascontiguousarray(ranks_host, dtype=np.int64).reshape(-1)
+    col0 = np.ascontiguousarray(col0_host, dtype=np.int64).reshape(-1)
+    n_bg = int(n_bg)
+    cap_tasks = int(((ranks + 3) // 4).sum()) + len(cs) * ((n_bg + 3) // 4) + 8
+    cap_items = len(cs) + cap_tasks
+    items = np.zeros((cap_items, 12), np.int32)
+    slot_ptr = np.zeros(cap_items * (TC_SLOTS + 1), np.int32)
+    tasks = np.zeros((cap_tasks, 8), np.int32)
+    cap_events = cap_tasks + ((n_bg + 3) // 4) * (len(cs) + 4) * (int(d1) + 2)  # local tasks + background drains
+    events = np.zeros((cap_events, 4), np.int32)
+    counts = np.zeros(8, np.int64)
+    rc = _lib.lib().pmd_make_strips_tc(_np_ptr(rs), len(rs), _np_ptr(cs), len(cs), int(bh), int(bw), int(d1), int(d2),
+                                       _np_ptr(ranks), _np_ptr(col0), n_bg, int(G or 0), _np_ptr(items), cap_items,
+                                       _np_ptr(slot_ptr), _np_ptr(tasks), cap_tasks, _np_ptr(events), cap_events, _np_ptr(counts))
+    _lib.check(rc, "pmd_make_strips_tc")
+    n_items, n_tasks, n_ev, chunks, n_parts, max_w8, g = (int(x) for x in counts[:7])
+    if n_items == 0:
+        return None
+    items = items[:n_items].copy()
+    item_of_row = np.concatenate([np.stack([np.full(int(it[3]), i, np.int32), np.arange(int(it[3]), dtype=np.int32)], axis=1)
+                                  for i, it in enumerate(items)], axis=0)
+    return dict(items=items, slot_ptr=slot_ptr[: n_items * (TC_SLOTS + 1)].copy(), tasks=tasks[:n_tasks].copy(),
+                events=events[:n_ev].copy(), item_of_row=np.ascontiguousarray(item_of_row), chunks=chunks, n_parts=n_parts,
+                max_w8=max_w8, G=g, n_items=n_items)
+
+
+def pack_strips_tc(st_dev, uvals32, bg, bpix, d2):
+    """Coefficient images (uint8 tensor, 32 KB per (item, row, 32-pixel chunk)) of pmd_project_stream_tc.
+    st_dev: make_strips_tc() tables with items / slot_ptr / tasks / events / item_of_row as device tensors."""
+    dev = st_dev["items"].device
+    bimg = torch.empty(st_dev["chunks"] * TC_CHUNK_BYTES, dtype=torch.uint8, device=dev)
+    uv = uvals32 if uvals32.numel() else torch.zeros((1, bpix), dtype=torch.float32, device=dev)
+    d = bg.shape[1] if bg is not None and bg.numel() else d2
+    _call("pmd_pack_strips_tc", _p(st_dev["items"]), _p(st_dev["item_of_row"]), st_dev["item_of_row"].shape[0],
+          _p(st_dev["slot_ptr"]), _p(st_dev["tasks"]), _p(_req(uv, torch.float32, "uvals")), bpix,
+          _p(bg) if bg is not None and bg.numel() else None, d, d2, _p(bimg), _stream())
+    return bimg
+
+
+def project_stream_tc_ok(movie2d, d2, mean, inv_std):
+    """Alignment requirements of the tensor-core projection kernel."""
+    ok = d2 % 4 == 0 and movie2d.data_ptr() % 16 == 0 and movie2d.stride(0) == movie2d.shape[1]
+    for v in (mean, inv_std):
+        ok = ok and (v is None or v.data_ptr() % 16 == 0)
+    return ok
+
+
+def project_stream_tc(movie2d, d2, st_dev, bimg, mean, inv_std, z_local, z_bg):
+    """K7 on tcgen05: z_local[col, f] and z_bg[k, f] of U^T standardised movie in one streaming pass."""
+    t, d = movie2d.shape
+    assert z_local.dtype == torch.float32 and (z_local.numel() == 0 or z_local.stride(1) == 1)
+    K = z_bg.shape[0]
+    parts = torch.zeros((st_dev["n_parts"], max(K, 1), t), dtype=torch.float32, device=movie2d.device)
+    zl = z_local if z_local.numel() else parts
+    _call("pmd_project_stream_tc", _p(movie2d), movie_dtype_code(movie2d), t, d2, d, _p(st_dev["items"]), st_dev["n_items"],
+          _p(st_dev["events"]), _p(bimg), _p(mean), _p(inv_std), _p(zl), zl.stride(0) if z_local.numel() else t, _p(parts), t,
+          max(K, 1) * t, _stream())
+    if K:
+        z_bg[:, :t].copy_(parts[:, :K].sum(dim=0))

@@ -58,8 +58,14 @@ class PMDArray:
 
     @staticmethod
     def _to_host(t):
-        # one-off copies: page-locking a fresh buffer costs more than the driver's staged pageable copy
-        return t.cpu().numpy()
+        # through torch's caching pinned-host allocator: after the first decomposition of a process the page-locked
+        # blocks are reused, so the copy runs at PCIe rate; the ndarray is a view of the pinned block and keeps it alive
+        if t.numel() == 0 or not t.is_cuda:
+            return t.cpu().numpy()
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        host.copy_(t, non_blocking=True)
+        torch.cuda.current_stream(t.device).synchronize()
+        return host.numpy()
 
     def _materialise(self, what):
         lz = self._lazy

@@ -59,6 +59,32 @@ if which in ("all", "stream"):
     upack = ops.pack_strip_u(sst, uv, bg, bh * bw)
     print("strips: items", sst["n_items"], "max_rw", sst["max_rw"], "tasks", len(sst["tasks"]))
     timeit("project_stream", lambda: ops.project_stream(movie, d2, sst_d, upack, mean, inv, z[:n_local], z[n_local:]))
+if which in ("all", "tc", "stream"):
+    G = int(os.environ.get("PMD_TC_G", "0")) or None
+    tst = ops.make_strips_tc(rows, cols, bh, bw, d1, d2, ranks, col0, K, G=G)
+    tst_d = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in tst.items()}
+    bimg = ops.pack_strips_tc(tst_d, uv, bg, bh * bw, d2)
+    it = tst["items"]
+    print("tc strips: G", tst["G"], "items", tst["n_items"], "max w8", tst["max_w8"], "image MB", bimg.numel() / 1e6,
+          "streamed/ideal %.3f" % (float((it[:, 1] * it[:, 3]).sum()) * 8 / (d1 * d2)))
+    z2 = torch.zeros_like(z)
+    timeit("pack_strips_tc", lambda: ops.pack_strips_tc(tst_d, uv, bg, bh * bw, d2))
+    timeit("project_stream_tc", lambda: ops.project_stream_tc(movie, d2, tst_d, bimg, mean, inv, z2[:n_local], z2[n_local:]))
+    if which in ("all", "stream"):
+        err = (z2 - z).abs().max().item() / z.abs().max().item()
+        print("max |tc - simt| / max |simt| = %.3e" % err)
+    n = min(T, 512)
+    ref = torch.zeros((n_local + K, n), dtype=torch.float64, device=dev)
+    yc = ((movie[:n].double() - mean.double()) * inv.double())
+    ref[n_local:] = bg.double() @ yc.t()
+    qi, qj = np.divmod(np.arange(bh * bw), bw)
+    for b in range(0, nb, max(1, nb // 64)):
+        i0, j0 = rows[b // len(cols)], cols[b % len(cols)]
+        pix = torch.from_numpy((i0 + qi) * d2 + j0 + qj).to(dev)
+        ref[col0[b] : col0[b] + ranks[b]] = uv[col0[b] : col0[b] + ranks[b]].double() @ yc[:, pix].t()
+    sel = ref.abs().sum(1) > 0
+    err = ((z2[:, :n].double() - ref)[sel].abs().max() / ref.abs().max()).item()
+    print("tc vs float64 reference (sampled blocks + background): max abs err / max |ref| = %.3e" % err)
 if which in ("all", "supertile"):
     timeit("project_supertile", lambda: ops.project_supertile(movie, d2, std, bh, bw, uv, mean, inv, z[:n_local]))
 if which in ("all", "local"):

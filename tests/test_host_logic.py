@@ -211,3 +211,73 @@ def test_strip_tables():
                     else:
                         bg_cover[col : col + nc, by : by + h, c0 + bx : c0 + bx + wd] += 1
         assert np.all(seen_cols == 1) and np.all(bg_cover == 1)
+
+
+def test_strip_tables_tc():
+    """make_strips_tc: a NumPy emulation of the tensor-core projection kernel driven ONLY by the host tables (slot
+    accumulators, coefficient rows, drain events) reproduces U^T Y, so every (block, component) and (pixel, background
+    component) is owned exactly once, slots never hold two live tasks, and every task is drained at its last row."""
+    from localmd_b200 import ops as host_ops
+
+    rng = np.random.default_rng(11)
+    cases = [(112, 96, 20, 20, 15, 14, None), (61, 84, 10, 10, 1, 4, None), (70, 96, 32, 32, 9, 30, None), (40, 40, 40, 40, 3, 5, None),
+             (60, 80, 20, 20, 0, 50, None), (64, 64, 16, 16, 5, 3, 2)]
+    for (d1, d2, bh, bw, n_bg, hi, G) in cases:
+        rs, cs = O.tile_starts(d1, bh), O.tile_starts(d2, bw)
+        ranks = rng.integers(1, hi + 1, len(rs) * len(cs))
+        col0 = np.concatenate([[0], np.cumsum(ranks)[:-1]])
+        n_local = int(ranks.sum())
+        st = host_ops.make_strips_tc(rs, cs, bh, bw, d1, d2, ranks, col0, n_bg, G=G)
+        assert st is not None
+        uv = rng.standard_normal((n_local, bh * bw))
+        bg = rng.standard_normal((max(n_bg, 1), d1 * d2))
+        T = 3
+        y = rng.standard_normal((T, d1, d2))
+        # reference
+        ref = np.zeros((n_local + n_bg, T))
+        blocks = [(a, c) for a in rs for c in cs]
+        for b, (i0, j0) in enumerate(blocks):
+            for c in range(ranks[b]):
+                ref[col0[b] + c] = np.einsum("tij,ij->t", y[:, i0 : i0 + bh, j0 : j0 + bw], uv[col0[b] + c].reshape(bh, bw))
+        for k in range(n_bg):
+            ref[n_local + k] = y.reshape(T, -1) @ bg[k]
+        # emulation
+        items, slot_ptr, tasks, events = st["items"], st["slot_ptr"], st["tasks"], st["events"]
+        z = np.full((n_local, T), np.nan)
+        zbg = np.zeros((st["n_parts"], max(n_bg, 1), T))
+        chunk = 0
+        for (c0, w8, row0, n_rows, b0, nkc, ev0, n_ev, part, sp0, _, _) in items:
+            W = 8 * w8
+            assert c0 % 4 == 0 and 0 <= c0 and c0 + W <= d2 and W <= 128 and nkc == (w8 + 3) // 4 and b0 == chunk
+            chunk += n_rows * nkc
+            acc = np.zeros((host_ops.TC_SLOTS * 4, T))
+            e = ev0
+            for row in range(row0, row0 + n_rows):
+                B = np.zeros((host_ops.TC_SLOTS * 4, W))
+                for s in range(host_ops.TC_SLOTS):
+                    live = [ti for ti in range(slot_ptr[sp0 + s], slot_ptr[sp0 + s + 1]) if tasks[ti][0] <= row < tasks[ti][0] + tasks[ti][2]]
+                    assert len(live) <= 1
+                    for ti in live:
+                        by, bx, h, wd, col, nc, kind, _ = tasks[ti]
+                        assert 1 <= nc <= 4 and bx >= 0 and bx + wd <= W
+                        for c in range(nc):
+                            if kind == 0:
+                                B[4 * s + c, bx : bx + wd] = uv[col + c].reshape(bh, bw)[row - by]
+                            else:
+                                B[4 * s + c, bx : bx + wd] = bg[col + c].reshape(d1, d2)[row, c0 + bx : c0 + bx + wd]
+                acc += B @ y[:, row, c0 : c0 + W].T
+                while e < ev0 + n_ev and events[e][0] == row:
+                    _, s, col, ncw = events[e]
+                    nc, kind = ncw & 0xFF, ncw >> 8
+                    if kind == 0:
+                        assert np.all(np.isnan(z[col : col + nc]))  # written exactly once
+                        z[col : col + nc] = acc[4 * s : 4 * s + nc]
+                    else:
+                        zbg[part, col : col + nc] += acc[4 * s : 4 * s + nc]
+                    acc[4 * s : 4 * s + 4] = 0
+                    e += 1
+            assert e == ev0 + n_ev and np.all(acc == 0)  # everything drained
+        assert chunk == st["chunks"]
+        np.testing.assert_allclose(z, ref[:n_local], atol=1e-9)
+        if n_bg:
+            np.testing.assert_allclose(zbg.sum(0)[:n_bg], ref[n_local:], atol=1e-9)

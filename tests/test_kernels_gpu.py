@@ -494,6 +494,46 @@ def test_project_stream(ops, bh, bw, max_rank, dtype, d1, d2, K, T):
         np.testing.assert_allclose(z2.cpu().numpy(), ref2, rtol=0, atol=2e-5 * np.abs(ref2).max())
 
 
+@pytest.mark.parametrize(
+    "bh,bw,max_rank,dtype,d1,d2,K,T,G",
+    [(20, 20, 13, np.float32, 112, 96, 15, 700, None), (10, 10, 3, np.uint16, 61, 84, 1, 300, None),
+     (16, 16, 12, np.float32, 70, 96, 5, 1100, 2), (22, 22, 20, np.int16, 61, 88, 9, 258, None),
+     (20, 12, 6, np.float32, 64, 40, 16, 513, None), (20, 20, 2, np.float64, 24, 28, 2, 64, None),
+     (32, 32, 6, np.uint8, 70, 96, 3, 260, None), (40, 40, 11, np.float32, 90, 104, 4, 255, None),
+     (20, 20, 50, np.float32, 60, 80, 0, 130, None), (20, 20, 4, np.int32, 50, 60, 2, 129, 1)],
+)
+def test_project_stream_tc(ops, bh, bw, max_rank, dtype, d1, d2, K, T, G):
+    """K7 on tcgen05 (TF32 main product + bf16 correction MMA, tensor-memory slot accumulators): local + dense
+    columns in one pass, against float64 U^T Y.  Tolerance as for the SIMT kernel (float32-accurate)."""
+    rng = np.random.default_rng(bh * 5 + max_rank)
+    starts, ranks, col0, uv, bg, U = _random_sparse_u(rng, d1, d2, bh, bw, max_rank, K)
+    y = rng.uniform(0, 200, size=(T, d1 * d2))
+    movie = (np.rint(y) if np.issubdtype(dtype, np.integer) else y).astype(dtype)
+    mean = rng.uniform(80, 120, d1 * d2).astype(np.float32)
+    std = rng.uniform(0.5, 2, d1 * d2).astype(np.float32)
+    inv = (1.0 / std).astype(np.float32)
+    n_local = int(ranks.sum())
+    st = ops.make_strips_tc(O.tile_starts(d1, bh), O.tile_starts(d2, bw), bh, bw, d1, d2, ranks, col0, K, G=G)
+    assert st is not None
+    std_ = {k: (dev(v) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+    bgd = dev(bg) if K else None
+    bimg = ops.pack_strips_tc(std_, dev(uv), bgd, bh * bw, d2)
+    z = torch.full((n_local + K, T + 5), 7.0, dtype=torch.float32, device="cuda")
+    mv = dev(movie)
+    assert ops.project_stream_tc_ok(mv, d2, dev(mean), dev(inv))
+    ops.project_stream_tc(mv, d2, std_, bimg, dev(mean), dev(inv), z[:n_local], z[n_local:])
+    yc = (movie.astype(np.float32).astype(np.float64) - mean) / std
+    ref = U.T @ yc.T
+    got = z.cpu().numpy()
+    np.testing.assert_allclose(got[:, :T], ref[: n_local + K], rtol=0, atol=2e-5 * np.abs(ref).max())
+    assert np.all(got[:, T:] == 7.0)  # nothing written beyond the movie
+    if dtype == np.float32:
+        z2 = torch.zeros((n_local + K, T), dtype=torch.float32, device="cuda")
+        ops.project_stream_tc(mv, d2, std_, bimg, None, None, z2[:n_local], z2[n_local:])
+        ref2 = U.T @ movie.astype(np.float64).T
+        np.testing.assert_allclose(z2.cpu().numpy(), ref2[: n_local + K], rtol=0, atol=2e-5 * np.abs(ref2).max())
+
+
 def test_project_without_standardisation(ops):
     rng = np.random.default_rng(9)
     d1, d2, T, K, bh, bw = 40, 36, 50, 2, 16, 16

@@ -272,7 +272,7 @@ def run_ours(args):
             traffic = tr.get("dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "pmd_project_stream (K7: U^T standardised movie, local + background columns)",
+    roofline = {"bound": "hbm", "kernel": "pmd_project_stream_tc (K7 on tcgen05: U^T standardised movie, local + background columns)",
                 "achieved": achieved, "peak": peak, "peak_source": "measured" if peaks else "fallback", "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "ms": k7_ms, "algorithmic_bytes": alg_bytes,
                 "projection_pass_ms": pass_ms, "n_cols": n_cols}
@@ -284,9 +284,10 @@ def run_ours(args):
         del movie, shard  # the freed HBM stays in torch's pool (a warm process would not re-cudaMalloc 21 GB per movie)
         src = host_t.numpy() if world == 1 else DeviceMovie.from_host_shard(host_t, t_total, lo, dev)
         e2e_runs = []
-        # one untimed warm-up pass (page-locked staging buffers, library handles), then timed passes: every pass copies
+        # untimed warm-up passes (page-locked staging buffers, library handles), then timed passes: every pass copies
         # the whole movie host -> device and reads every factor of the result + one reconstructed frame back
-        for it_e2e in range(1 + max(1, min(2, args.steps))):
+        n_warm_e2e = 2  # the second warm pass re-uses the page-locked result buffers the first one released
+        for it_e2e in range(n_warm_e2e + max(1, min(2, args.steps))):
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             t0 = time.perf_counter()
@@ -309,17 +310,19 @@ def run_ours(args):
             if args.stage_times and rank == 0:
                 sys.stderr.write("e2e stage ms: %s  wall %.1f ms\n" % (
                     json.dumps({k: round(v, 2) for k, v in det.items() if isinstance(v, float) and "." not in k}), wall * 1e3))
-            if it_e2e > 0:
+            if it_e2e >= n_warm_e2e:
                 e2e_runs.append(max(e0.elapsed_time(e1), wall * 1e3))
+            if rank == 0:
+                d2h = int(arr.u.data.nbytes + arr.u.indices.nbytes + arr.u.indptr.nbytes + arr.r.nbytes + arr.s.nbytes
+                          + arr.v.nbytes + 2 * 4 * d1 * d2 + frame.nbytes)
+                del result, frame
+            del arr  # page-locked result buffers go back to torch's host cache for the next pass
         e2e_ms = float(np.mean(e2e_runs))
         if world > 1:
             tt = torch.tensor([e2e_ms], device=dev)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             e2e_ms = float(tt.item())
         if rank == 0:
-            d2h = int(arr.u.data.nbytes + arr.u.indices.nbytes + arr.u.indptr.nbytes + arr.r.nbytes + arr.s.nbytes + arr.v.nbytes
-                      + 2 * 4 * d1 * d2 + frame.nbytes)
-            del result
             e2e = {"value": t_total / (e2e_ms / 1e3), "unit": "frames/s",
                    "h2d_bytes_per_step": int(det.get("__info__", {}).get("h2d_bytes", host_t.numel() * host_t.element_size())) * world,
                    "d2h_bytes_per_step": d2h, "ms": e2e_ms, "passes": len(e2e_runs)}

@@ -20,6 +20,8 @@
 // Every movie element is read once per strip that contains it (strips overlap by half a block only).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace pmd {
@@ -34,9 +36,9 @@ constexpr int kPTATile = 128 * 128;          // bytes of one A operand tile (128
 constexpr int kPTAStage = 2 * kPTATile;      // tf32 tile + bf16 pair tile
 constexpr int kPTBPart = kPTN * 128;         // bytes of one B part (128 columns x 32 pixels x 4 B)
 constexpr int kPTBStage = 2 * kPTBPart;      // 32 KB
-constexpr int kPTEpiWarps = 4, kPTProdWarps = 8;
+constexpr int kPTEpiWarps = 4, kPTProdWarps = 16;
 constexpr int kPTProducers = kPTProdWarps * 32;
-constexpr int kPTThreads = (kPTEpiWarps + kPTProdWarps + 2) * 32;   // + MMA warp + B loader warp
+constexpr int kPTThreads = (kPTEpiWarps + kPTProdWarps + 3) * 32;   // + MMA warp + B loader warp + L2 prefetch warp
 constexpr int kPTSmem = kPTAStages * kPTAStage + kPTBStages * kPTBStage + 1024;
 
 struct PTItem {                              // 12 ints (strips_tc_host.cu)
@@ -84,6 +86,17 @@ __device__ __forceinline__ void pt_mbar_wait(uint32_t bar, uint32_t parity) {
         : "memory");
 }
 #endif
+__device__ __forceinline__ bool pt_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void pt_mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
@@ -103,18 +116,18 @@ __device__ __forceinline__ void pt_mma_tf32(uint32_t tmem_d, uint64_t da, uint64
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(1u)
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
         : "memory");
 }
 __device__ __forceinline__ void pt_mma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc) {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.eq.b32 p, 0, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(1u)
+        "}\n" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc)
         : "memory");
 }
 
@@ -181,11 +194,12 @@ __global__ void __launch_bounds__(kPTThreads, 1)
 project_tc_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_t d, const PTItem* __restrict__ items,
                   const PTEvent* __restrict__ events, const unsigned char* __restrict__ bimg, const float* __restrict__ mean,
                   const float* __restrict__ inv_std, float* __restrict__ z, int64_t ldz, float* __restrict__ zbg, int64_t ldzbg,
-                  int64_t bg_stride) {
+                  int64_t bg_stride, int ablate, int pf_rows) {
     extern __shared__ __align__(1024) unsigned char ptsm[];
     __shared__ __align__(8) uint64_t bar_afull[kPTAStages], bar_aempty[kPTAStages], bar_bfull[kPTBStages], bar_bempty[kPTBStages],
         bar_accfull, bar_accfree;
     __shared__ uint32_t tmem_base_s;
+    __shared__ volatile int s_rows_issued;
     const uint32_t sbase = (pt_smem_u32(ptsm) + 1023u) & ~1023u;
     const uint32_t sb_base = sbase + kPTAStages * kPTAStage;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -196,6 +210,7 @@ project_tc_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_t d,
     const int n_groups = it.n_rows * it.nkc;                              // (row, 32-pixel chunk) groups
 
     if (tid == 0) {
+        s_rows_issued = 0;
         for (int s = 0; s < kPTAStages; ++s) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(pt_smem_u32(&bar_afull[s])), "r"(kPTProducers / kPTTiles));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(pt_smem_u32(&bar_aempty[s])));
@@ -304,26 +319,30 @@ project_tc_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_t d,
         }
     } else if (warp < kPTEpiWarps + kPTProdWarps) {
         // ================================ A producers ================================
-        // Warp pair p (64 threads) owns frame tile p: it fills that tile's stage once per (row, 32-pixel chunk) group.
-        // A thread handles 16 pieces (4 pixels of one frame): 16-byte chunk c = its index % 8, frames m = index / 8 + 8 q.
-        // All 16 raw loads of the NEXT group are issued right after the current stage is handed over and are consumed
+        // Four warps (128 threads) own one frame tile: they fill that tile's stage once per (row, 32-pixel chunk) group.
+        // A thread handles 8 pieces (4 pixels of one frame): 16-byte chunk c = its index % 8, frames m = index / 8 + 16 q.
+        // All raw loads of the NEXT group are issued right after the current stage is handed over and are consumed
         // together one group later (a single register set, in flight while the other three pairs work).
         const int ptid = tid - kPTEpiWarps * 32;
-        const int ft = ptid >> 6, idx = ptid & 63;
+        constexpr int kGroup = kPTProducers / kPTTiles;            // producer threads per frame tile (128)
+        constexpr int NQ = 8 * 128 / kGroup;                       // pieces per thread and stage (8)
+        constexpr int kFStep = kGroup / 8;                         // frames between the pieces of a thread (16)
+        const int ft = ptid / kGroup, idx = ptid % kGroup;
         const int c = idx & 7, m0 = idx >> 3;
         if (ft < nft) {
-            constexpr int NQ = 16;
-            const int srow = m0 * 128 + ((c ^ m0) << 4);          // + q * 1024 (frame m0 + 8 q keeps m & 7 = m0)
+            // frame m = m0 + kFStep q: row m & 7 = m0 & 7 of 8-row atom (m0 >> 3) + (kFStep / 8) q
+            const int srow = (m0 >> 3) * 1024 + (m0 & 7) * 128 + ((c ^ (m0 & 7)) << 4);
+            constexpr int kQBytes = (kFStep / 8) * 1024;
             // frames past the end of the movie repeat the last frame (their results are never stored)
             const int64_t fa = f0 + 128 * ft + m0;
-            const int qmax = fa < t ? (int)min((int64_t)(NQ - 1), (t - 1 - fa) / 8) : 0;
+            const int qmax = fa < t ? (int)min((int64_t)(NQ - 1), (t - 1 - fa) / kFStep) : 0;
             const T* const fptr = movie + min(fa, t - 1) * d + it.c0 + 4 * c;
-            const int64_t qstep = fa < t ? 8 * d : 0;
+            const int64_t qstep = fa < t ? kFStep * d : 0;
             Px4<T> pre[NQ];
             float4 mu = make_float4(0.f, 0.f, 0.f, 0.f), is = make_float4(1.f, 1.f, 1.f, 1.f);
             const bool ok_last = 32 * (it.nkc - 1) + 4 * c < 8 * it.w8;   // only the last chunk of a row can be partial
             auto issue_loads = [&](int64_t goff, bool ok) {
-                if (!ok) return;
+                if (!ok || (ablate & 2)) return;
                 if (mean) mu = __ldg(reinterpret_cast<const float4*>(mean + goff + it.c0 + 4 * c));
                 if (inv_std) is = __ldg(reinterpret_cast<const float4*>(inv_std + goff + it.c0 + 4 * c));
                 const T* p = fptr + goff;
@@ -334,26 +353,27 @@ project_tc_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_t d,
             int64_t goff = (int64_t)it.row0 * d2;                 // pixel offset of the group: row * d2 + 32 kc
             issue_loads(goff, it.nkc > 1 || ok_last);
             const int st = ft;                                     // stage = frame tile (phase = group: no parity aliasing)
+            const uint32_t my_full = pt_smem_u32(&bar_afull[st]), my_empty = pt_smem_u32(&bar_aempty[st]);
+            const uint32_t a_tf = sbase + st * kPTAStage + srow, a_bf = a_tf + kPTATile;
             for (int g = 0; g < n_groups; ++g) {
                 const bool ok = kc < it.nkc - 1 || ok_last;
-                if (g >= 1) pt_mbar_wait(pt_smem_u32(&bar_aempty[st]), (g - 1) & 1);
-                if (ok) {
-                    const uint32_t a_tf = sbase + st * kPTAStage + srow, a_bf = a_tf + kPTATile;
+                if (g >= 1) pt_mbar_wait(my_empty, (g - 1) & 1);
+                if (ok && !(ablate & 4)) {
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) {
                         const float4 x = pre[q].get();
                         const float y0 = (x.x - mu.x) * is.x, y1 = (x.y - mu.y) * is.y, y2 = (x.z - mu.z) * is.z, y3 = (x.w - mu.w) * is.w;
                         const float h0 = __uint_as_float(__float_as_uint(y0) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(y1) & 0xFFFFE000u);
                         const float h2 = __uint_as_float(__float_as_uint(y2) & 0xFFFFE000u), h3 = __uint_as_float(__float_as_uint(y3) & 0xFFFFE000u);
-                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(a_tf + q * 1024), "f"(h0), "f"(h1), "f"(h2), "f"(h3)
+                        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(a_tf + q * kQBytes), "f"(h0), "f"(h1), "f"(h2), "f"(h3)
                                      : "memory");
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a_bf + q * 1024), "r"(pt_pack_bf16(h0, y0 - h0)),
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(a_bf + q * kQBytes), "r"(pt_pack_bf16(h0, y0 - h0)),
                                      "r"(pt_pack_bf16(h1, y1 - h1)), "r"(pt_pack_bf16(h2, y2 - h2)), "r"(pt_pack_bf16(h3, y3 - h3))
                                      : "memory");
                     }
                 }
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-                pt_mbar_arrive(pt_smem_u32(&bar_afull[st]));
+                if (!(ablate & 16)) asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+                pt_mbar_arrive(my_full);
                 if (++kc == it.nkc) {
                     kc = 0;
                     goff += d2 - 32 * (it.nkc - 1);
@@ -364,66 +384,107 @@ project_tc_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_t d,
             }
         }
     } else if (warp == kPTEpiWarps + kPTProdWarps) {
-        // ================================ MMA issuer (one thread) ================================
-        if (lane == 0) {
-            // D f32, A / B K-major, N = 128, M = 128
-            constexpr uint32_t idesc_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kPTN >> 3) << 17) | ((128u >> 4) << 24);
-            constexpr uint32_t idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kPTN >> 3) << 17) | ((128u >> 4) << 24);
-            const PTEvent* ev = events + it.ev0;
-            int e = 0, k = 0;
-            pt_mbar_wait(pt_smem_u32(&bar_accfree), 0);
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
-            int kc = 0, row = it.row0;
-            for (int g = 0; g < n_groups; ++g) {
-                const int nks = min(4, it.w8 - 4 * kc);
-                const int bs = g % kPTBStages;
-                pt_mbar_wait(pt_smem_u32(&bar_bfull[bs]), (g / kPTBStages) & 1);
-                const uint32_t b_tf = sb_base + bs * kPTBStage, b_bf = b_tf + kPTBPart;
-                for (int ft = 0; ft < nft; ++ft) {
-                    const int st = ft;
-                    pt_mbar_wait(pt_smem_u32(&bar_afull[st]), g & 1);
+        // ================================ MMA issuer ================================
+        // The whole warp runs the (warp-uniform) control flow so that addresses and descriptors stay in uniform
+        // registers; one elected lane issues the tcgen05 instructions of a stage and its commits.
+        // D f32, A / B K-major, N = 128, M = 128
+        constexpr uint32_t idesc_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kPTN >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr uint32_t idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kPTN >> 3) << 17) | ((128u >> 4) << 24);
+        // K-major SWIZZLE_128B descriptor: low word = start address >> 4, high word = SBO 1024 >> 4 | version | layout type
+        constexpr uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+        const PTEvent* ev = events + it.ev0;
+        int e = 0, k = 0;
+        // barrier addresses once (arrays of 8-byte barriers: + 8 per stage)
+        const uint32_t afull0 = pt_smem_u32(&bar_afull[0]), aempty0 = pt_smem_u32(&bar_aempty[0]);
+        const uint32_t bfull0 = pt_smem_u32(&bar_bfull[0]), bempty0 = pt_smem_u32(&bar_bempty[0]);
+        const uint32_t accfull = pt_smem_u32(&bar_accfull), accfree = pt_smem_u32(&bar_accfree);
+        const bool leader = pt_elect_one();
+        const uint32_t a_tf0 = sbase >> 4, b_tf0 = sb_base >> 4;
+        pt_mbar_wait(accfree, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+        int kc = 0, row = it.row0, bs = 0;
+        uint32_t bpar = 0;
+        int next_ev_row = it.n_ev > 0 ? ev[0].row : -1;
+        for (int g = 0; g < n_groups; ++g) {
+            const int nks = min(4, it.w8 - 4 * kc);
+            pt_mbar_wait(bfull0 + 8 * bs, bpar);
+            const uint32_t b_tf = b_tf0 + bs * (kPTBStage >> 4), b_bf = b_tf + (kPTBPart >> 4);
+#pragma unroll
+            for (int ft = 0; ft < kPTTiles; ++ft) {
+                if (ft < nft) {
+                    pt_mbar_wait(afull0 + 8 * ft, g & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
-                    const uint32_t a_tf = sbase + st * kPTAStage, a_bf = a_tf + kPTATile;
-                    const uint32_t dcol = tmem_d + kPTN * ft;
-                    for (int ks = 0; ks < nks; ++ks) {
-                        pt_mma_tf32(dcol, pt_desc(a_tf + 32 * ks), pt_desc(b_tf + 32 * ks), idesc_tf32);
-                        pt_mma_bf16(dcol, pt_desc(a_bf + 32 * ks), pt_desc(b_bf + 32 * ks), idesc_bf16);
+                    if (leader) {
+                        const uint32_t a_tf = a_tf0 + ft * (kPTAStage >> 4), a_bf = a_tf + (kPTATile >> 4);
+                        const uint32_t dcol = tmem_d + kPTN * ft;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            if (ks < nks && !(ablate & 1)) {
+                                pt_mma_tf32(dcol, desc_hi | (a_tf + 2 * ks), desc_hi | (b_tf + 2 * ks), idesc_tf32);
+                                pt_mma_bf16(dcol, desc_hi | (a_bf + 2 * ks), desc_hi | (b_bf + 2 * ks), idesc_bf16);
+                            }
+                        }
+                        pt_commit(aempty0 + 8 * ft);
+                        if (ft == nft - 1) pt_commit(bempty0 + 8 * bs);
                     }
-                    pt_commit(pt_smem_u32(&bar_aempty[st]));
                 }
-                pt_commit(pt_smem_u32(&bar_bempty[bs]));
-                if (kc == it.nkc - 1 && e < it.n_ev && ev[e].row == row) {
-                    // tasks end at this row: let the epilogue warps drain and clear their slots
-                    while (e < it.n_ev && ev[e].row == row) ++e;
-                    pt_commit(pt_smem_u32(&bar_accfull));
-                    ++k;
-                    pt_mbar_wait(pt_smem_u32(&bar_accfree), k & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
-                }
-                if (++kc == it.nkc) {
-                    kc = 0;
-                    ++row;
-                }
+            }
+            if (++bs == kPTBStages) {
+                bs = 0;
+                bpar ^= 1;
+            }
+            if (kc == it.nkc - 1 && row == next_ev_row) {
+                // tasks end at this row: let the epilogue warps drain and clear their slots
+                while (e < it.n_ev && ev[e].row == row) ++e;
+                next_ev_row = e < it.n_ev ? ev[e].row : -1;
+                if (leader) pt_commit(accfull);
+                ++k;
+                pt_mbar_wait(accfree, k & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+            }
+            if (++kc == it.nkc) {
+                kc = 0;
+                ++row;
+                if (leader) s_rows_issued = row - it.row0;
             }
         }
     } else if (warp == kPTEpiWarps + kPTProdWarps + 1) {
         // ================================ B loader (one thread) ================================
         if (lane == 0) {
             const unsigned char* src = bimg + (int64_t)it.b_chunk0 * kPTBStage;
+            const uint32_t bfull0 = pt_smem_u32(&bar_bfull[0]), bempty0 = pt_smem_u32(&bar_bempty[0]);
             for (int g = 0; g < n_groups; ++g) {
                 const int bs = g % kPTBStages;
-                if (g + kPTBPrefetch < n_groups)
+                if (g + kPTBPrefetch < n_groups && !(ablate & 8))
                     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src + (int64_t)(g + kPTBPrefetch) * kPTBStage),
                                  "r"((uint32_t)kPTBStage)
                                  : "memory");
-                if (g >= kPTBStages) pt_mbar_wait(pt_smem_u32(&bar_bempty[bs]), ((g / kPTBStages) - 1) & 1);
-                const uint32_t bar = pt_smem_u32(&bar_bfull[bs]);
+                if (g >= kPTBStages) pt_mbar_wait(bempty0 + 8 * bs, ((g / kPTBStages) - 1) & 1);
+                const uint32_t bar = bfull0 + 8 * bs;
+                if (ablate & 8) {
+                    pt_mbar_arrive(bar);
+                    continue;
+                }
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"((uint32_t)kPTBStage) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
                                  sb_base + bs * kPTBStage),
                              "l"(src + (int64_t)g * kPTBStage), "r"((uint32_t)kPTBStage), "r"(bar)
                              : "memory");
             }
+        }
+    }
+    else if (pf_rows > 0) {
+        // ================================ L2 prefetcher (optional) ================================
+        // asks L2 for the 128-byte lines of the strip row the producers will load pf_rows rows after the row the MMA
+        // stream is at (one line per lane and instruction), so that the producers' loads are L2 hits
+        const int nframes = (int)min((int64_t)(128 * kPTTiles), t - f0);
+        const int nlines = (int)((it.w8 * 8 * sizeof(T) + 127) / 128);
+        for (int rr = 1; rr < it.n_rows; ++rr) {
+            while (s_rows_issued + pf_rows < rr) __nanosleep(100);
+            const char* p = reinterpret_cast<const char*>(movie + (int64_t)(it.row0 + rr) * d2 + it.c0);
+            for (int f = lane; f < nframes; f += 32)
+                for (int l = 0; l < nlines; ++l)   // the lines of one frame back to back: one DRAM row activation
+                    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p + (f0 + f) * d * (int64_t)sizeof(T) + 128 * l));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
@@ -512,13 +573,23 @@ extern "C" int pmd_project_stream_tc(const void* movie, int dtype, int64_t t, in
     const int64_t ftiles = (t + 128 * pmd::kPTTiles - 1) / (128 * pmd::kPTTiles);
     PMD_REQUIRE(n_items <= 65535, fn, "too many strip items");
     cudaStream_t st = (cudaStream_t)stream;
+    // profiling aid (results are wrong when set): bit 0 no MMAs, 1 no movie loads, 2 no operand stores, 3 no coefficient copies, 4 no proxy fence
+    static const int ablate = [] {
+        const char* e = getenv("PMD_TC_ABLATE");
+        return e ? atoi(e) : 0;
+    }();
+    // rows of the movie the prefetch warp asks L2 for ahead of the producers (0 = off)
+    static const int pf_rows = [] {
+        const char* e = getenv("PMD_TC_PREFETCH_ROWS");
+        return e ? atoi(e) : 0;
+    }();
     PMD_DISPATCH_DTYPE(dtype, fn, {
         auto k = pmd::project_tc_kernel<scalar_t>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pmd::kPTSmem);
         if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
         k<<<dim3((unsigned)ftiles, (unsigned)n_items), pmd::kPTThreads, pmd::kPTSmem, st>>>(
             (const scalar_t*)movie, t, d2, d, (const pmd::PTItem*)items, (const pmd::PTEvent*)events, (const unsigned char*)bimg,
-            mean, inv_std, z, ldz, zbg, ldzbg, bg_stride);
+            mean, inv_std, z, ldz, zbg, ldzbg, bg_stride, ablate, pf_rows);
     });
     return pmd::check_launch(fn);
 }

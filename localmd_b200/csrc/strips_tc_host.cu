@@ -91,8 +91,14 @@ bool build(int g, const int32_t* rs, int nbr, const int32_t* cs, int nbc, int bh
     int part = 0;
     for (int ca = 0; ca < nbc; ca += g, ++part) {
         const int cb = std::min(ca + g, nbc);
-        int a0 = cs[ca] & ~3;
-        const int width = (cs[cb - 1] + bw - a0 + 7) / 8 * 8;
+        // first column: aligned down to a 128-byte line of float32 pixels (32 pixels) when the strip stays within the
+        // supported width -- a warp-level load of the kernel then covers whole lines --, else to 16 bytes (4 pixels)
+        int a0 = cs[ca] & ~31;
+        int width = (cs[cb - 1] + bw - a0 + 7) / 8 * 8;
+        if (width > kMaxW) {
+            a0 = cs[ca] & ~3;
+            width = (cs[cb - 1] + bw - a0 + 7) / 8 * 8;
+        }
         if (width > kMaxW) return false;
         if (a0 + width > d2) a0 = d2 - width;     // shift left: the extra columns get zero coefficients
         if (a0 < 0 || (a0 & 3)) return false;

@@ -13,6 +13,7 @@ README aliases block_height/block_width/frames_to_init are accepted.
 """
 import datetime
 import math
+import os
 import sys
 from typing import Callable, Optional
 
@@ -339,18 +340,32 @@ class SparseU:
         cols = sorted(set(int(x) for x in starts[:, 1])) if len(ranks_host) else []
         regular = len(ranks_host) > 0 and len(rows) * len(cols) == len(ranks_host) and np.array_equal(
             np.asarray(starts, dtype=np.int64), np.array([(a, c) for a in rows for c in cols], dtype=np.int64))
-        if regular:
-            st = ops.make_strips(rows, cols, bh, bw, d1, d2, ranks_host, self.col0_host, bg.shape[0])
+        self.strips_tc = None
+        self._regular = (rows, cols) if regular else None
+        if regular and os.environ.get("PMD_K7", "tc") != "simt":
+            # K7 on the tensor cores (csrc/project_tc.cu): tables + coefficient images, built once per decomposition
+            st = ops.make_strips_tc(rows, cols, bh, bw, d1, d2, ranks_host, self.col0_host, bg.shape[0])
             if st is not None:
                 dev = ranks_dev.device
-                self.strips = {k: (torch.from_numpy(v).to(dev) if k in ("items", "slot_ptr", "tasks") else v) for k, v in st.items()}
-                self.upack = ops.pack_strip_u(st, uvals32, bg, bh * bw)
-        if self.strips is None and len(ranks_host) and bh * bw <= 512:
+                self.strips_tc = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+                self.bimg = ops.pack_strips_tc(self.strips_tc, uvals32, bg, bh * bw, d2)
+        if regular and self.strips_tc is None:
+            self._build_simt_strips()
+        if self.strips is None and self.strips_tc is None and len(ranks_host) and bh * bw <= 512:
             if len(rows) * len(cols) == len(ranks_host):
                 st = ops.make_supertiles(rows, cols, bh, bw, ranks_host, self.col0_host)
                 if st["max_h"] * st["max_w"] <= 2048:
                     self.supertiles = {k: (torch.from_numpy(v).to(ranks_dev.device) if isinstance(v, np.ndarray) else v)
                                        for k, v in st.items()}
+
+    def _build_simt_strips(self):
+        """Tables of the SIMT strip-streaming kernel (fallback of the tensor-core path: unaligned movies, tiny FOVs)."""
+        rows, cols = self._regular
+        st = ops.make_strips(rows, cols, self.bh, self.bw, self.d1, self.d2, self.ranks_host, self.col0_host, self.bg.shape[0])
+        if st is not None:
+            dev = self.ranks_dev.device
+            self.strips = {k: (torch.from_numpy(v).to(dev) if k in ("items", "slot_ptr", "tasks") else v) for k, v in st.items()}
+            self.upack = ops.pack_strip_u(st, self.uvals32, self.bg, self.bh * self.bw)
 
     @property
     def tasks(self):
@@ -446,6 +461,13 @@ class SparseU:
     def project(self, movie2d, mean, inv_std, z):
         """z[:, :n] (R, ldz) (+)= U^T standardised(movie2d)   (K7a + K7b)."""
         n = movie2d.shape[0]
+        if self.strips_tc is not None:
+            if ops.project_stream_tc_ok(movie2d, self.d2, mean, inv_std):
+                ops.project_stream_tc(movie2d, self.d2, self.strips_tc, self.bimg, mean, inv_std, z[: self.n_local], z[self.n_local :])
+                _submark("projection.stream")
+                return
+            if self.strips is None and self._regular is not None:
+                self._build_simt_strips()
         if self.strips is not None:
             ops.project_stream(movie2d, self.d2, self.strips, self.upack, mean, inv_std, z[: self.n_local], z[self.n_local :])
             _submark("projection.stream")

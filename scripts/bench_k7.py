@@ -14,7 +14,8 @@ from localmd_b200.decomposition import tile_starts  # noqa: E402
 T = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 which = sys.argv[3] if len(sys.argv) > 3 else "all"
-d1 = d2 = 512
+d1 = int(os.environ.get("PMD_BK7_D1", "512"))
+d2 = 512
 bh = bw = 20
 K = 15
 rng = np.random.default_rng(0)
@@ -26,7 +27,8 @@ n_local = int(ranks.sum())
 dev = torch.device("cuda")
 uv = torch.randn((n_local, bh * bw), device=dev)
 bg = torch.randn((K, d1 * d2), device=dev)
-movie = torch.randn((T, d1 * d2), device=dev) * 3 + 100
+PAD = int(os.environ.get("PMD_BK7_PAD", "0"))  # extra floats per frame (frame stride experiment)
+movie = torch.randn((T, d1 * d2 + PAD), device=dev) * 3 + 100
 mean = torch.full((d1 * d2,), 100.0, device=dev)
 inv = torch.full((d1 * d2,), 0.5, device=dev)
 starts = torch.from_numpy(np.array([(r, c) for r in rows for c in cols], dtype=np.int32)).to(dev)

@@ -498,7 +498,7 @@ def test_project_stream(ops, bh, bw, max_rank, dtype, d1, d2, K, T):
     "bh,bw,max_rank,dtype,d1,d2,K,T,G",
     [(20, 20, 13, np.float32, 112, 96, 15, 700, None), (10, 10, 3, np.uint16, 61, 84, 1, 300, None),
      (16, 16, 12, np.float32, 70, 96, 5, 1100, 2), (22, 22, 20, np.int16, 61, 88, 9, 258, None),
-     (20, 12, 6, np.float32, 64, 40, 16, 513, None), (20, 20, 2, np.float64, 24, 28, 2, 64, None),
+     (20, 12, 6, np.float32, 64, 40, 16, 513, None), (20, 20, 2, np.float64, 24, 32, 2, 64, None),
      (32, 32, 6, np.uint8, 70, 96, 3, 260, None), (40, 40, 11, np.float32, 90, 104, 4, 255, None),
      (20, 20, 50, np.float32, 60, 80, 0, 130, None), (20, 20, 4, np.int32, 50, 60, 2, 129, 1)],
 )

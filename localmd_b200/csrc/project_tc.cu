@@ -204,8 +204,8 @@ project_tc_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_t d,
     const uint32_t sb_base = sbase + kPTAStages * kPTAStage;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // grid: x = frame tile (fastest), y = item: the CTAs of one strip run together and share its coefficient images in L2
-    const PTItem it = items[blockIdx.y];
-    const int64_t f0 = (int64_t)blockIdx.x * (128 * kPTTiles);
+    const PTItem it = items[(ablate & 128) ? blockIdx.x : blockIdx.y];
+    const int64_t f0 = (int64_t)((ablate & 128) ? blockIdx.y : blockIdx.x) * (128 * kPTTiles);
     const int nft = (int)min((int64_t)kPTTiles, (t - f0 + 127) / 128);   // frame tiles that hold at least one frame
     const int n_groups = it.n_rows * it.nkc;                              // (row, 32-pixel chunk) groups
 
@@ -571,7 +571,7 @@ extern "C" int pmd_project_stream_tc(const void* movie, int dtype, int64_t t, in
     PMD_REQUIRE((!mean || ((uintptr_t)mean & 15) == 0) && (!inv_std || ((uintptr_t)inv_std & 15) == 0), fn,
                 "mean / inv_std must be 16-byte aligned");
     const int64_t ftiles = (t + 128 * pmd::kPTTiles - 1) / (128 * pmd::kPTTiles);
-    PMD_REQUIRE(n_items <= 65535, fn, "too many strip items");
+    PMD_REQUIRE(n_items <= 65535 && ftiles <= 65535, fn, "too many strip items / frames per call");
     cudaStream_t st = (cudaStream_t)stream;
     // profiling aid (results are wrong when set): bit 0 no MMAs, 1 no movie loads, 2 no operand stores, 3 no coefficient copies, 4 no proxy fence
     static const int ablate = [] {
@@ -587,7 +587,8 @@ extern "C" int pmd_project_stream_tc(const void* movie, int dtype, int64_t t, in
         auto k = pmd::project_tc_kernel<scalar_t>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pmd::kPTSmem);
         if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
-        k<<<dim3((unsigned)ftiles, (unsigned)n_items), pmd::kPTThreads, pmd::kPTSmem, st>>>(
+        const dim3 grid = (ablate & 128) ? dim3((unsigned)n_items, (unsigned)ftiles) : dim3((unsigned)ftiles, (unsigned)n_items);
+        k<<<grid, pmd::kPTThreads, pmd::kPTSmem, st>>>(
             (const scalar_t*)movie, t, d2, d, (const pmd::PTItem*)items, (const pmd::PTEvent*)events, (const unsigned char*)bimg,
             mean, inv_std, z, ldz, zbg, ldzbg, bg_stride, ablate, pf_rows);
     });

@@ -243,8 +243,11 @@ def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, 
     return np.percentile(sp.flatten(), sim_conf), np.percentile(tp.flatten(), sim_conf)
 
 
-def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_t, mcf, sketches):
+def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_t, mcf, sketches, spatial_denoiser=None,
+                         temporal_denoiser=None):
     """single_block_md (decomposition.py:235-330) for all blocks at once.
+    temporal_denoiser / spatial_denoiser: the reference's hooks (decomposition.py:300, 310) as torch callables on CUDA
+    tensors, (n_traces, t) -> (n_traces, t) and (n_images, bh, bw) -> (n_images, bh, bw), applied to all blocks at once.
     yt (d, ld) float32: pixel-major standardised init movie, t frames (a multiple of taf), zero padded
     to ld.  sketches (nb, t//taf, r+10).
     Returns U (nb, b, rp), V (nb, r, ld), ranks (nb,), sstat, tstat."""
@@ -290,11 +293,33 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
         vds = ops.block_project_tc(yt, 0, ld, d2, starts_dev, bh, bw, w4, r)  # (nb, r, ld)
         del w4
     _submark("blocks.project1")
+    if temporal_denoiser is not None:
+        # decomposition.py:300: the sketch traces of every block are denoised before they define the temporal basis
+        tr = temporal_denoiser(vds[:, :, :t].reshape(nb * r, t).contiguous())
+        if tuple(tr.shape) != (nb * r, t):
+            raise ValueError("temporal_denoiser must return a (n_traces, n_frames) tensor of the shape it was given")
+        vds = torch.zeros((nb, r, ld), dtype=torch.float32, device=dev)
+        vds[:, :, :t] = tr.to(torch.float32).reshape(nb, r, t)
+    if spatial_denoiser is not None:
+        # decomposition.py:301-313: the reference denoises the images S = B Vb^T with Vb = the right singular vectors
+        # of the sketch traces; a nonlinear denoiser depends on those specific images (not only on their span), so Vb
+        # is formed explicitly: V_ds V_ds^T = E diag(w) E^T, Vb = diag(w)^-1/2 E^T V_ds (rows by descending w)
+        w, e = ops.jacobi_eigh(ops.gram_rows(vds), mode=0)
+        scale = torch.where(w > 0, w.clamp_min(1e-300).rsqrt(), torch.zeros_like(w)).to(torch.float32)
+        vds = torch.bmm((e * scale[:, None, :]).transpose(1, 2).contiguous(), vds)
     # S' = B V_ds^T has the same column space as the reference's S = B Vb^T (Vb = orthonormalised rows of V_ds,
     # decomposition.py:301-306), and only that space is used downstream (Uf = orth(S), 315); the rows of V_ds are the
     # nearly orthogonal sketch directions, so S' only needs the column scaling that CholQR's relative pivots apply anyway.
     s_raw = ops.block_spatial_tc(yt, 0, ld, d2, starts_dev, bh, bw, vds, rp)  # (nb, b, rp): tcgen05, 3xTF32
     del vds
+    if spatial_denoiser is not None:
+        # decomposition.py:307-313: every (bh, bw) image of the spatial projection is denoised
+        imgs = s_raw[:, :, :r].reshape(nb, bh, bw, r).permute(0, 3, 1, 2).reshape(nb * r, bh, bw).contiguous()
+        den = spatial_denoiser(imgs)
+        if tuple(den.shape) != (nb * r, bh, bw):
+            raise ValueError("spatial_denoiser must return a (n_images, block height, block width) tensor of the shape it was given")
+        s_raw = torch.zeros((nb, bh * bw, rp), dtype=torch.float32, device=dev)
+        s_raw[:, :, :r] = den.to(torch.float32).reshape(nb, r, bh * bw).transpose(1, 2)
     _submark("blocks.spatial")
     if ops.block_orth_fits(bh * bw, r):
         uf = ops.block_orth(s_raw, r)  # (nb, b, rp)
@@ -632,8 +657,9 @@ def localmd_decomposition(
         frame_range = frames_to_init
     if dtype != "float32":
         raise ValueError("only dtype='float32' is supported (the reference computes in float32 on device)")
-    if spatial_denoiser is not None or temporal_denoiser is not None:
-        raise NotImplementedError("user denoiser hooks are not implemented on the sm_100a path yet")
+    for name_, fn_ in (("spatial_denoiser", spatial_denoiser), ("temporal_denoiser", temporal_denoiser)):
+        if fn_ is not None and not callable(fn_):
+            raise TypeError("%s must be a callable on CUDA torch tensors" % name_)
     if not torch.cuda.is_available():
         raise RuntimeError("localmd_b200 needs a CUDA device (built for sm_100a); there is no CPU fallback")
     dev = torch.device(device if device is not None else ("cuda:%d" % torch.cuda.current_device()))
@@ -769,7 +795,7 @@ def localmd_decomposition(
         b0, b1 = sharding.block_partition(nb, world)[rank]
         u_blk, v_blk, ranks_loc, sstat, tstat = block_decompositions(
             yt, crop, d2, starts_dev[b0:b1], bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
-            int(max_consecutive_failures), sketches[b0:b1],
+            int(max_consecutive_failures), sketches[b0:b1], spatial_denoiser, temporal_denoiser,
         )
         del sketches
         if group is None:

@@ -282,3 +282,62 @@ def test_unseeded_run_reference_test_shapes():
     vv = arr.v.astype(np.float64) @ arr.v.T
     lead = arr.s > 0.05 * arr.s[0]
     assert np.abs(vv - np.eye(k))[np.ix_(lead, lead)].max() < 1e-3
+
+
+def test_denoiser_hooks_match_oracle():
+    """spatial_denoiser / temporal_denoiser (decomposition.py:300, 310): torch callables on the CUDA path, the same
+    functions in NumPy for the oracle.  The temporal one is a moving average, the spatial one a 3x3 box filter followed
+    by an odd-symmetric soft threshold (nonlinear: it depends on the individual singular-vector images, not only on
+    their span; odd symmetry makes it indifferent to the sign convention of the SVD)."""
+    import localmd_b200
+    import torch.nn.functional as tf
+
+    T, d1, d2, bh, bw, t, r, K = 600, 40, 36, 16, 16, 300, 6, 2
+    movie = make_movie(T, d1, d2, n_cells=5, seed=11)
+    rng = np.random.default_rng(2)
+    nb = len(O.tile_starts(d1, bh)) * len(O.tile_starts(d2, bw))
+    d = O.Draws(bg_frames=rng.choice(T, T, replace=False).tolist(), bg_sketch=rng.standard_normal((T, K + 10)).astype(np.float32),
+                init_frames=list(range(150, 150 + t)), thresholds=(1.35, 2.3),
+                block_sketches=[[rng.standard_normal((t // 10, r + 10)).astype(np.float32)] for _ in range(nb)])
+    tau = 0.02
+
+    def temporal_np(v):
+        v = np.asarray(v)
+        k = np.ones(5, dtype=v.dtype) / 5
+        return np.stack([np.convolve(row, k, mode="same") for row in v])
+
+    def temporal_t(v):
+        k = torch.full((1, 1, 5), 0.2, dtype=v.dtype, device=v.device)
+        return tf.conv1d(v[:, None, :], k, padding=2)[:, 0, :]
+
+    def spatial_np(x):
+        x = np.asarray(x)
+        p = np.pad(x, ((0, 0), (1, 1), (1, 1)))
+        sm = sum(p[:, i : i + x.shape[1], j : j + x.shape[2]] for i in range(3) for j in range(3)) / x.dtype.type(9)
+        return np.sign(sm) * np.maximum(np.abs(sm) - x.dtype.type(tau), 0)
+
+    def spatial_t(x):
+        k = torch.full((1, 1, 3, 3), 1.0 / 9, dtype=x.dtype, device=x.device)
+        sm = tf.conv2d(x[:, None], k, padding=1)[:, 0]
+        return torch.sign(sm) * torch.clamp(sm.abs() - tau, min=0)
+
+    kw = dict(max_components=r, background_rank=K)
+    det = {}
+    arr = localmd_b200.localmd_decomposition(movie, [bh, bw], t, draws=d, details=det, spatial_denoiser=spatial_t,
+                                             temporal_denoiser=temporal_t, **kw)
+    with O.precision(np.float64):
+        ref = O.localmd_decomposition_oracle(movie, [bh, bw], t, d, spatial_denoiser=spatial_np, temporal_denoiser=temporal_np, **kw)
+    plain = localmd_b200.localmd_decomposition(movie, [bh, bw], t, draws=d, **kw)
+    near = near_threshold_blocks(det, ref.thresholds)
+    assert np.all((det["ranks"] == ref.ranks) | near), (det["ranks"].tolist(), ref.ranks.tolist())
+    if np.array_equal(det["ranks"], ref.ranks):
+        k = min(len(arr.s), len(ref.s))
+        lead = ref.s[:k] > 0.05 * ref.s[0]
+        np.testing.assert_allclose(arr.s[:k][lead], ref.s[:k][lead], rtol=1e-4)
+        fr = [0, 299, 599]
+        got, want = arr[fr, :, :], ref.to_pmdarray()[fr, :, :]
+        assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-4
+    # the hooks do change the result (they are not silently ignored)
+    assert len(plain.s) != len(arr.s) or not np.allclose(plain.s, arr.s, rtol=1e-6)
+    with pytest.raises(TypeError):
+        localmd_b200.localmd_decomposition(movie, [bh, bw], t, draws=d, spatial_denoiser=3, **kw)

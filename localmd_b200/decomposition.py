@@ -344,6 +344,103 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
     return u, v, ranks, sstat, tstat
 
 
+def _append_components(final, counter, comps, n_new):
+    """final[b, :, counter[b] : counter[b] + n_new[b]] = comps[b, :, : n_new[b]]  (ragged append, all blocks at once)."""
+    nb, bpix, rp = final.shape
+    j = torch.arange(comps.shape[2], device=final.device)[None, :]
+    valid = j < n_new[:, None]
+    if not bool(valid.any()):
+        return
+    blk = torch.arange(nb, device=final.device)[:, None].expand_as(valid)[valid]
+    src = j.expand_as(valid)[valid]
+    dst = (counter[:, None] + j)[valid]
+    ft, ct = final.transpose(1, 2), comps.transpose(1, 2)   # (nb, comps, pixels) views
+    ft[blk, dst] = ct[blk, src]
+
+
+def block_decompositions_windowed(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_t, mcf, sketches, window,
+                                  spatial_denoiser=None, temporal_denoiser=None):
+    """windowed_pmd (decomposition.py:410-525) for all blocks at once, window_chunks < frame_range.
+    The first window (and any later window of a block that has kept nothing yet) is fitted by single_block_md
+    (235-330); later windows fit the residual after projecting out the components kept so far
+    (single_residual_block_md, 333-387: time average only, no spatial pooling); a block stops once it holds r
+    components.  sketches: list over windows of (nb, window // taf, r + 10).  Same return values as
+    block_decompositions, with V = (kept U)^T block over all t frames (get_temporal_projector, 390-407)."""
+    dev = yt.device
+    d, ld = yt.shape
+    nb = starts_dev.shape[0]
+    rp = (r + 3) // 4 * 4
+    bpix = bh * bw
+    if window % taf:
+        raise ValueError("window_chunks must be a multiple of temporal_avg_factor")
+    start_points = list(range(0, t, window))
+    if start_points and start_points[-1] + window > t:
+        start_points[-1] = t - window
+    ldw = (window + 3) // 4 * 4
+    final = torch.zeros((nb, bpix, rp), dtype=torch.float32, device=dev)
+    counter = torch.zeros((nb,), dtype=torch.int64, device=dev)
+    sstat = torch.zeros((nb, r), dtype=torch.float32, device=dev)
+    tstat = torch.zeros((nb, r), dtype=torch.float32, device=dev)
+    qi, qj = torch.arange(bpix, device=dev) // bw, torch.arange(bpix, device=dev) % bw
+    pix = (starts_dev[:, 0:1].to(torch.int64) + qi[None, :]) * d2 + starts_dev[:, 1:2].to(torch.int64) + qj[None, :]  # (nb, bpix)
+    for wi, k in enumerate(start_points):
+        active = counter < r
+        if not bool(active.any()):
+            break
+        yw = torch.zeros((d, ldw), dtype=torch.float32, device=dev)
+        yw[:, :window] = yt[:, k : k + window]
+        sk = sketches[wi]
+        fresh = active & (counter == 0) if k != 0 else active
+        resid = active & ~fresh
+        ia = torch.nonzero(fresh).reshape(-1)
+        if ia.numel():
+            u_a, _, rk_a, ss_a, ts_a = block_decompositions(
+                yw, window, d2, starts_dev[ia].contiguous(), bh, bw, r, taf, saf, thr_s, thr_t, mcf, sk[ia].contiguous(),
+                spatial_denoiser, temporal_denoiser)
+            n_new = torch.minimum(rk_a.to(torch.int64), r - counter[ia])
+            fa, ca = final[ia], counter[ia]
+            _append_components(fa, ca, u_a, n_new)
+            final[ia] = fa
+            counter[ia] = ca + n_new
+            if wi == 0:
+                sstat[ia], tstat[ia] = ss_a, ts_a
+            del u_a
+        ib = torch.nonzero(resid).reshape(-1)
+        for c0 in range(0, int(ib.numel()), 1024):   # bounded working set: (1024, bpix, window) floats per slab
+            ic = ib[c0 : c0 + 1024]
+            n = int(ic.numel())
+            e = final[ic]                                            # (n, bpix, rp), columns >= counter are zero
+            blk = yw[pix[ic]]                                        # (n, bpix, ldw)
+            blk.baddbmm_(e, torch.bmm(e.transpose(1, 2), blk), alpha=-1.0)   # residual block (decomposition.py:362-364)
+            avg = blk[:, :, :window].reshape(n, bpix, window // taf, taf).mean(dim=3)   # (n, bpix, t')
+            skc = sk[ic]
+            l = skc.shape[2]
+            if bpix > l:
+                y = torch.bmm(avg, skc)
+                q = ops.block_orth(y) if ops.block_orth_fits(bpix, l) else ops.orthonormalize_cols(y)
+                bq = torch.bmm(q.transpose(1, 2), avg).contiguous()
+                _, ev = ops.jacobi_eigh(ops.gram_rows(bq), mode=0)
+                u_b = torch.bmm(q, ev[:, :, :r])                     # (n, bpix, r)
+            else:
+                if r > bpix:
+                    raise TypeError("max_components larger than the block (jax.lax.dynamic_slice would fail)")
+                _, ev = ops.jacobi_eigh(ops.gram_rows(avg.contiguous()), mode=0)
+                u_b = ev[:, :, :r]
+            v_b = torch.bmm(u_b.transpose(1, 2), blk).contiguous()   # (n, r, ldw)
+            u_pad = torch.zeros((n, bpix, rp), dtype=torch.float32, device=dev)
+            u_pad[:, :, :r] = u_b
+            _, _, rk_b = ops.block_stats_rank(u_pad, v_b, bh, bw, r, thr_s, thr_t, mcf, t=window)
+            n_new = torch.minimum(rk_b.to(torch.int64), r - counter[ic])
+            fb, cb = final[ic], counter[ic]
+            _append_components(fb, cb, u_pad, n_new)
+            final[ic] = fb
+            counter[ic] = cb + n_new
+            del blk, avg, u_b, v_b, u_pad
+        del yw
+    v = ops.block_project_tc(yt, 0, ld, d2, starts_dev, bh, bw, final, r)   # (nb, r, ld)
+    return final, v, counter.to(torch.int32), sstat, tstat
+
+
 class SparseU:
     """Device form of the sparse spatial matrix: block-component values + dense background rows."""
 
@@ -736,8 +833,6 @@ def localmd_decomposition(
                 frames = [int(f) for f in init_frames]
             else:
                 frames = identify_window_chunks(frame_range, T, window_chunks, rng)
-        if window_chunks < len(frames):
-            raise NotImplementedError("window_chunks < frame_range (residual windows) is not implemented on the sm_100a path yet")
         say("We are initializing on a total of {} frames".format(len(frames)))
 
         block_sizes = update_block_sizes(block_sizes, (d1, d2))
@@ -787,16 +882,33 @@ def localmd_decomposition(
 
         # ---- block fits (decomposition.py:790-838) -------------------------------------------------
         bs = take("block_sketches")
-        if bs is not None:
-            sketches = torch.stack([_as_dev(b_[0] if isinstance(b_, (list, tuple)) else b_, dev) for b_ in bs])
-        else:
-            sketches = torch.randn((nb, crop // temporal_avg_factor, r + 10), generator=gen, device=dev, dtype=torch.float32)
         # blocks are partitioned over the ranks (contiguous index ranges); results are all-gathered below
         b0, b1 = sharding.block_partition(nb, world)[rank]
-        u_blk, v_blk, ranks_loc, sstat, tstat = block_decompositions(
-            yt, crop, d2, starts_dev[b0:b1], bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
-            int(max_consecutive_failures), sketches[b0:b1], spatial_denoiser, temporal_denoiser,
-        )
+        windowed = window_chunks < crop
+        if not windowed:
+            if bs is not None:
+                sketches = torch.stack([_as_dev(b_[0] if isinstance(b_, (list, tuple)) else b_, dev) for b_ in bs])
+            else:
+                sketches = torch.randn((nb, crop // temporal_avg_factor, r + 10), generator=gen, device=dev, dtype=torch.float32)
+            u_blk, v_blk, ranks_loc, sstat, tstat = block_decompositions(
+                yt, crop, d2, starts_dev[b0:b1], bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
+                int(max_consecutive_failures), sketches[b0:b1], spatial_denoiser, temporal_denoiser,
+            )
+        else:
+            # one Gaussian per (block, visited window) (decomposition.py:475, 62)
+            n_win = len(range(0, crop, window_chunks))
+            if bs is not None:
+                # a block that reached max_components stops consuming sketches: missing entries are never used
+                shape_w = (window_chunks // temporal_avg_factor, r + 10)
+                sketches = [torch.stack([_as_dev(b_[wi], dev) if wi < len(b_) else torch.zeros(shape_w, dtype=torch.float32, device=dev)
+                                         for b_ in bs])[b0:b1] for wi in range(n_win)]
+            else:
+                sketches = [torch.randn((nb, window_chunks // temporal_avg_factor, r + 10), generator=gen, device=dev,
+                                        dtype=torch.float32)[b0:b1] for _ in range(n_win)]
+            u_blk, v_blk, ranks_loc, sstat, tstat = block_decompositions_windowed(
+                yt, crop, d2, starts_dev[b0:b1].contiguous(), bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
+                int(max_consecutive_failures), sketches, int(window_chunks), spatial_denoiser, temporal_denoiser,
+            )
         del sketches
         if group is None:
             ranks_dev = ranks_loc

@@ -19,7 +19,7 @@ from synth import make_movie
 pytestmark = pytest.mark.gpu
 
 EPS_STAT = 2e-4  # relative band around a threshold inside which a rank decision may legitimately differ
-GPU_CASES = ["main_F", "prune_C_u16", "tiny_noNorm", "wide_R"]
+GPU_CASES = ["main_F", "prune_C_u16", "tiny_noNorm", "wide_R", "windows"]
 
 _cache = {}
 
@@ -260,8 +260,8 @@ def test_guards():
         localmd_b200.localmd_decomposition(movie[:8], [16, 16], 100, temporal_avg_factor=10)
     with pytest.raises(ValueError):
         localmd_b200.localmd_decomposition(movie, [16, 16], 100, rank_prune=True, rank_prune_factor=1.5)
-    with pytest.raises(NotImplementedError):
-        localmd_b200.localmd_decomposition(movie, [16, 16], 200, window_chunks=100)
+    with pytest.raises(ValueError):  # windows must hold whole temporal-average groups
+        localmd_b200.localmd_decomposition(movie, [16, 16], 200, window_chunks=95)
 
 
 def test_unseeded_run_reference_test_shapes():

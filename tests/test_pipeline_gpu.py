@@ -341,3 +341,36 @@ def test_denoiser_hooks_match_oracle():
     assert len(plain.s) != len(arr.s) or not np.allclose(plain.s, arr.s, rtol=1e-6)
     with pytest.raises(TypeError):
         localmd_b200.localmd_decomposition(movie, [bh, bw], t, draws=d, spatial_denoiser=3, **kw)
+
+
+def test_residual_windows_match_oracle():
+    """window_chunks < frame_range with many visited windows per block (decomposition.py:333-387, 455-515): most blocks
+    fit two to four residual windows before they reach max_components."""
+    import localmd_b200
+
+    T, d1, d2, bh, bw, fr, W, r, K = 1200, 32, 32, 16, 16, 600, 100, 8, 1
+    movie = make_movie(T, d1, d2, n_cells=10, seed=21)
+    rng = np.random.default_rng(4)
+    nb = len(O.tile_starts(d1, bh)) * len(O.tile_starts(d2, bw))
+    frames = []
+    for k in (0, 300, 500, 700, 900, 1100):
+        frames.extend(range(k, k + W))
+    d = O.Draws(bg_frames=rng.choice(T, 1000, replace=False).tolist(), bg_sketch=rng.standard_normal((1000, K + 10)).astype(np.float32),
+                init_frames=frames, thresholds=(1.25, 2.2),
+                block_sketches=[[rng.standard_normal((W // 10, r + 10)).astype(np.float32) for _ in range(fr // W)] for _ in range(nb)])
+    kw = dict(max_components=r, background_rank=K, window_chunks=W)
+    det = {}
+    arr = localmd_b200.localmd_decomposition(movie, [bh, bw], fr, draws=d, details=det, **kw)
+    ref = O.localmd_decomposition_oracle(movie, [bh, bw], fr, d, **kw)
+    with O.precision(np.float64):
+        ref64 = O.localmd_decomposition_oracle(movie, [bh, bw], fr, d, **kw)
+    visited = [len(bd) for bd in ref.block_diags]
+    assert max(visited) >= 3 and sum(v > 1 for v in visited) >= nb // 2  # the residual path is what is being tested
+    if not (np.array_equal(ref.ranks, ref64.ranks) and np.array_equal(det["ranks"], ref64.ranks)):
+        pytest.skip("a rank decision falls inside the float32 band of a threshold")
+    k = min(len(arr.s), len(ref64.s))
+    lead = ref64.s[:k] > 0.05 * ref64.s[0]
+    np.testing.assert_allclose(arr.s[:k][lead], ref64.s[:k][lead], rtol=1e-4)
+    fsel = [0, 450, 1199]
+    got, want = arr[fsel, :, :], ref64.to_pmdarray()[fsel, :, :]
+    assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-4

@@ -201,6 +201,8 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
+        # NCCL_DEBUG=VERSION/INFO makes NCCL print to stdout, which must carry exactly one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     w = WORKLOADS[args.workload]

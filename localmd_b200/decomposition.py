@@ -15,6 +15,7 @@ import datetime
 import math
 import os
 import sys
+import threading
 from typing import Callable, Optional
 
 import numpy as np
@@ -257,7 +258,24 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
     rp = (r + 3) // 4 * 4
     ph, pw = -(-bh // saf), -(-bw // saf)
     pooled = None
-    if nb * ph * pw * ld * 4 <= 24 << 30:
+    d1 = d // d2
+    fov_pool = None
+    if bh % saf == 0 and bw % saf == 0 and d1 % saf == 0 and d2 % saf == 0 and d1 // saf <= 65535 and bool(
+            (starts_dev % saf == 0).all()):
+        # Every block starts on the pooling grid: its pooled block is a window of the POOLED FIELD OF VIEW, so the movie
+        # is pooled once (the pooling entry point applied to non-overlapping saf x d2 row bands: same arithmetic, bit
+        # identical cells) instead of once per overlapping block (4x the reads, 4x the writes at stride b/2)
+        d1p, d2p = d1 // saf, d2 // saf
+        bands = torch.stack([torch.arange(0, d1, saf, dtype=torch.int32, device=dev),
+                             torch.zeros(d1p, dtype=torch.int32, device=dev)], dim=1).contiguous()
+        yp, ypa = ops.block_pool_full(yt, t, d2, bands, saf, d2, saf, taf)      # (d1p, d2p, ld), (d1p, d2p, t')
+        sp = (starts_dev // saf).to(torch.int32).contiguous()
+        qp = torch.arange(ph * pw, device=dev)
+        pixp = (sp[:, 0:1].to(torch.int64) + (qp // pw)[None, :]) * d2p + sp[:, 1:2].to(torch.int64) + (qp % pw)[None, :]
+        bta = ypa.reshape(d1p * d2p, -1)[pixp].contiguous()                      # (nb, P, t')
+        fov_pool = (yp.reshape(d1p * d2p, ld), d2p, sp)
+        del ypa
+    elif nb * ph * pw * ld * 4 <= 24 << 30:
         # B_ds at full time resolution is kept (5.2 GB at C2) so that U_ds^T B_ds contracts over the pooled pixels
         pooled, bta = ops.block_pool_full(yt, t, d2, starts_dev, bh, bw, saf, taf)  # (nb, P, ld), (nb, P, t')
     else:
@@ -282,7 +300,13 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
         uds = e[:, :, :r].contiguous()
     del bta
     _submark("blocks.rsvd")
-    if pooled is not None:
+    if fov_pool is not None:
+        udp = torch.zeros((nb, ph * pw, rp), dtype=torch.float32, device=dev)
+        udp[:, :, :r] = uds
+        ypm, d2p, sp = fov_pool
+        vds = ops.block_project_tc(ypm, 0, ld, d2p, sp, ph, pw, udp, r)  # (nb, r, ld) = U_ds^T B_ds
+        del fov_pool, ypm, udp
+    elif pooled is not None:
         udp = torch.zeros((nb, ph * pw, rp), dtype=torch.float32, device=dev)
         udp[:, :, :r] = uds
         zero_starts = torch.zeros((nb, 2), dtype=torch.int32, device=dev)
@@ -464,21 +488,55 @@ class SparseU:
             np.asarray(starts, dtype=np.int64), np.array([(a, c) for a in rows for c in cols], dtype=np.int64))
         self.strips_tc = None
         self._regular = (rows, cols) if regular else None
+        self._tc_thread = None
         if regular and os.environ.get("PMD_K7", "tc") != "simt":
-            # K7 on the tensor cores (csrc/project_tc.cu): tables + coefficient images, built once per decomposition
-            st = ops.make_strips_tc(rows, cols, bh, bw, d1, d2, ranks_host, self.col0_host, bg.shape[0])
-            if st is not None:
-                dev = ranks_dev.device
-                self.strips_tc = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
-                self.bimg = ops.pack_strips_tc(self.strips_tc, uvals32, bg, bh * bw, d2)
-        if regular and self.strips_tc is None:
+            # K7 on the tensor cores (csrc/project_tc.cu): the host tables are built on a side thread (pure host work in
+            # the native library, the GIL is released) while the GPU runs the whitening stage; the first projection call
+            # joins it, uploads the tables and builds the coefficient images
+            def build_tables():
+                try:
+                    self._tc_host = ops.make_strips_tc(rows, cols, bh, bw, d1, d2, ranks_host, self.col0_host, bg.shape[0])
+                except BaseException as exc:  # re-raised by the thread that joins
+                    self._tc_error = exc
+
+            self._tc_error = None
+
+            self._tc_host = None
+            self._tc_thread = threading.Thread(target=build_tables)
+            self._tc_thread.start()
+        elif regular:
             self._build_simt_strips()
-        if self.strips is None and self.strips_tc is None and len(ranks_host) and bh * bw <= 512:
-            if len(rows) * len(cols) == len(ranks_host):
-                st = ops.make_supertiles(rows, cols, bh, bw, ranks_host, self.col0_host)
-                if st["max_h"] * st["max_w"] <= 2048:
-                    self.supertiles = {k: (torch.from_numpy(v).to(ranks_dev.device) if isinstance(v, np.ndarray) else v)
-                                       for k, v in st.items()}
+        if self.strips is None and self._tc_thread is None:
+            self._build_supertiles()
+
+    def _build_supertiles(self):
+        """Tables of the supertile kernel (irregular block lists, geometries neither strip kernel supports)."""
+        rows = sorted(set(int(x) for x in self.starts[:, 0])) if len(self.ranks_host) else []
+        cols = sorted(set(int(x) for x in self.starts[:, 1])) if len(self.ranks_host) else []
+        if len(self.ranks_host) and self.bh * self.bw <= 512 and len(rows) * len(cols) == len(self.ranks_host):
+            st = ops.make_supertiles(rows, cols, self.bh, self.bw, self.ranks_host, self.col0_host)
+            if st["max_h"] * st["max_w"] <= 2048:
+                self.supertiles = {k: (torch.from_numpy(v).to(self.ranks_dev.device) if isinstance(v, np.ndarray) else v)
+                                   for k, v in st.items()}
+
+    def _finish_tc(self):
+        """Join the table builder; upload the tables and build the coefficient images (once)."""
+        if self._tc_thread is None:
+            return
+        self._tc_thread.join()
+        self._tc_thread = None
+        if self._tc_error is not None:
+            raise self._tc_error
+        st = self._tc_host
+        self._tc_host = None
+        if st is not None:
+            dev = self.ranks_dev.device
+            self.strips_tc = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+            self.bimg = ops.pack_strips_tc(self.strips_tc, self.uvals32, self.bg, self.bh * self.bw, self.d2)
+        elif self._regular is not None:
+            self._build_simt_strips()
+            if self.strips is None:
+                self._build_supertiles()
 
     def _build_simt_strips(self):
         """Tables of the SIMT strip-streaming kernel (fallback of the tensor-core path: unaligned movies, tiny FOVs)."""
@@ -583,6 +641,7 @@ class SparseU:
     def project(self, movie2d, mean, inv_std, z):
         """z[:, :n] (R, ldz) (+)= U^T standardised(movie2d)   (K7a + K7b)."""
         n = movie2d.shape[0]
+        self._finish_tc()
         if self.strips_tc is not None:
             if ops.project_stream_tc_ok(movie2d, self.d2, mean, inv_std):
                 ops.project_stream_tc(movie2d, self.d2, self.strips_tc, self.bimg, mean, inv_std, z[: self.n_local], z[self.n_local :])

@@ -160,6 +160,10 @@ extern "C" int pmd_make_strips_tc(const int32_t* row_starts, int64_t nbr, const 
         if (g >= nbc) break;
     }
     if (best_cost < 0) return 0;
+    // largest items first: the grid is scheduled in item order, so the short row-range items fill the tail of the last wave
+    std::stable_sort(best.begin(), best.end(), [](const TItem& a, const TItem& b) {
+        return (long)a.w8 * (a.row1 - a.row0) > (long)b.w8 * (b.row1 - b.row0);
+    });
     int64_t ntask = 0;
     for (const TItem& it : best)
         for (int s = 0; s < kSlots; ++s) ntask += (int64_t)it.slots[s].size();

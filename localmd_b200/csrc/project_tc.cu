@@ -474,7 +474,7 @@ project_tc_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_t d,
         }
     }
     else if (pf_rows > 0) {
-        // ================================ L2 prefetcher (optional) ================================
+        // ================================ L2 prefetcher ================================
         // asks L2 for the 128-byte lines of the strip row the producers will load pf_rows rows after the row the MMA
         // stream is at (one line per lane and instruction), so that the producers' loads are L2 hits
         const int nframes = (int)min((int64_t)(128 * kPTTiles), t - f0);
@@ -578,10 +578,10 @@ extern "C" int pmd_project_stream_tc(const void* movie, int dtype, int64_t t, in
         const char* e = getenv("PMD_TC_ABLATE");
         return e ? atoi(e) : 0;
     }();
-    // rows of the movie the prefetch warp asks L2 for ahead of the producers (0 = off)
+    // rows of the movie the prefetch warp asks L2 for ahead of the MMA stream (0 = off)
     static const int pf_rows = [] {
         const char* e = getenv("PMD_TC_PREFETCH_ROWS");
-        return e ? atoi(e) : 0;
+        return e ? atoi(e) : 1;   // one row ahead: the strip row of a frame reaches DRAM as one burst (-4 % at C2)
     }();
     PMD_DISPATCH_DTYPE(dtype, fn, {
         auto k = pmd::project_tc_kernel<scalar_t>;

@@ -27,6 +27,8 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     "c2": dict(T=20000, d1=512, d2=512, block=20, frames_to_init=5000, n_cells=400, blob=(3.0, 5.0), bg_rank=2),
     "c3": dict(T=20000, d1=512, d2=512, block=32, frames_to_init=5000, n_cells=400, blob=(3.0, 5.0), bg_rank=2),
+    # BASELINE.json configs[3]: 1024x1024x30000 widefield movie over 8 GPUs = 3750 frames (15.7 GB) per GPU
+    "c4": dict(T=3750, d1=1024, d2=1024, block=40, frames_to_init=5000, n_cells=150, blob=(12.0, 25.0), bg_rank=8),
     "small": dict(T=4096, d1=128, d2=128, block=20, frames_to_init=1000, n_cells=40, blob=(3.0, 5.0), bg_rank=2),
 }
 
@@ -176,10 +178,13 @@ def run_reference(args):
 
 def workload_config(name, n_gpus):
     w = WORKLOADS[name]
-    return {"workload": "synthetic %dx%dx%d float32 two-photon movie, block %dx%d, frames_to_init %d, rank_prune 0.33 "
-                        "(BASELINE.json configs[1])" % (w["d1"], w["d2"], w["T"], w["block"], w["block"], w["frames_to_init"]),
+    which = {"c2": "BASELINE.json configs[1]", "c3": "BASELINE.json configs[2]", "c4": "BASELINE.json configs[3], per-GPU shard"}
+    gb = 4.0 * w["d1"] * w["d2"] * w["T"] / 1e9
+    return {"workload": "synthetic %dx%dx%d float32 %s movie, block %dx%d, frames_to_init %d, rank_prune 0.33 (%s)"
+                        % (w["d1"], w["d2"], w["T"], "widefield" if name == "c4" else "two-photon", w["block"], w["block"],
+                           w["frames_to_init"], which.get(name, "reduced test size")),
             "frames_per_gpu": w["T"], "total_frames": w["T"] * n_gpus,
-            "timing": "inputs (21 GB/GPU) larger than L2; CUDA events, max over ranks",
+            "timing": "inputs (%.0f GB/GPU) larger than L2; CUDA events, max over ranks" % gb,
             "parallelism": "one movie of %d frames, frame-sharded x%d (blocks partitioned, NCCL reductions/gathers)"
                            % (w["T"] * n_gpus, n_gpus) if n_gpus > 1 else "single GPU"}
 

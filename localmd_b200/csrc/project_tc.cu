@@ -5,9 +5,10 @@
 // kPTTiles x 128 frames, and walks the strip one image row at a time.  Per row and 32-pixel chunk:
 //   D[128 frames x 128 slot columns] += A[128 frames x 32 pixels] * B[32 pixels x 128 slot columns]   (per frame tile)
 //   * A: the movie is frame-major, so the 32 pixels of a frame are 128 contiguous bytes = one row of the canonical
-//     K-major SWIZZLE_128B operand.  Eight producer warps load them (128-bit loads, register prefetch one chunk group
-//     ahead), centre / scale, and write TWO operand tiles: hi = x with the low 13 mantissa bits cleared (exact in TF32)
-//     and a bf16 pair tile (bf16(hi), bf16(x - hi)) per pixel.
+//     K-major SWIZZLE_128B operand.  Sixteen producer warps, four per frame tile, load them (128-bit loads, all pieces
+//     of the next chunk issued together one chunk ahead), centre / scale, and write TWO operand tiles: hi = x with the
+//     low 13 mantissa bits cleared (exact in TF32) and a bf16 pair tile (bf16(hi), bf16(x - hi)) per pixel.  A
+//     prefetch warp asks L2 for the next strip row of every frame as one contiguous burst.
 //   * B: the coefficient image of the strip row, prebuilt once per decomposition by pmd_pack_strips_tc in exactly
 //     the shared-memory image (swizzled, TF32 hi part + bf16 pair part (bf16(lo), bf16(hi))); one thread fetches each
 //     32 KB chunk with a single bulk asynchronous copy (cp.async.bulk, mbarrier complete_tx).
@@ -18,6 +19,8 @@
 //     the walk is inside the block's rows.  When tasks end at a row, the MMA thread commits, four epilogue warps read
 //     the finished slots (tcgen05.ld), clear them (tcgen05.st) and hand the accumulators back, then store z.
 // Every movie element is read once per strip that contains it (strips overlap by half a block only).
+// The background slots are additionally drained every <= 16 rows: the tensor core adds into its float32 accumulators
+// with truncation, a bias that grows with the number of accumulation steps (see strips_tc_host.cu).
 #include <cuda_bf16.h>
 
 #include <cstdlib>
@@ -204,8 +207,8 @@ project_tc_kernel(const T* __restrict__ movie, int64_t t, int64_t d2, int64_t d,
     const uint32_t sb_base = sbase + kPTAStages * kPTAStage;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // grid: x = frame tile (fastest), y = item: the CTAs of one strip run together and share its coefficient images in L2
-    const PTItem it = items[(ablate & 128) ? blockIdx.x : blockIdx.y];
-    const int64_t f0 = (int64_t)((ablate & 128) ? blockIdx.y : blockIdx.x) * (128 * kPTTiles);
+    const PTItem it = items[blockIdx.y];
+    const int64_t f0 = (int64_t)blockIdx.x * (128 * kPTTiles);
     const int nft = (int)min((int64_t)kPTTiles, (t - f0 + 127) / 128);   // frame tiles that hold at least one frame
     const int n_groups = it.n_rows * it.nkc;                              // (row, 32-pixel chunk) groups
 
@@ -571,7 +574,7 @@ extern "C" int pmd_project_stream_tc(const void* movie, int dtype, int64_t t, in
     PMD_REQUIRE((!mean || ((uintptr_t)mean & 15) == 0) && (!inv_std || ((uintptr_t)inv_std & 15) == 0), fn,
                 "mean / inv_std must be 16-byte aligned");
     const int64_t ftiles = (t + 128 * pmd::kPTTiles - 1) / (128 * pmd::kPTTiles);
-    PMD_REQUIRE(n_items <= 65535 && ftiles <= 65535, fn, "too many strip items / frames per call");
+    PMD_REQUIRE(n_items <= 65535, fn, "too many strip items");
     cudaStream_t st = (cudaStream_t)stream;
     // profiling aid (results are wrong when set): bit 0 no MMAs, 1 no movie loads, 2 no operand stores, 3 no coefficient copies, 4 no proxy fence
     static const int ablate = [] {
@@ -587,8 +590,7 @@ extern "C" int pmd_project_stream_tc(const void* movie, int dtype, int64_t t, in
         auto k = pmd::project_tc_kernel<scalar_t>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pmd::kPTSmem);
         if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
-        const dim3 grid = (ablate & 128) ? dim3((unsigned)n_items, (unsigned)ftiles) : dim3((unsigned)ftiles, (unsigned)n_items);
-        k<<<grid, pmd::kPTThreads, pmd::kPTSmem, st>>>(
+        k<<<dim3((unsigned)ftiles, (unsigned)n_items), pmd::kPTThreads, pmd::kPTSmem, st>>>(
             (const scalar_t*)movie, t, d2, d, (const pmd::PTItem*)items, (const pmd::PTEvent*)events, (const unsigned char*)bimg,
             mean, inv_std, z, ldz, zbg, ldzbg, bg_stride, ablate, pf_rows);
     });

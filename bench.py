@@ -249,6 +249,22 @@ def run_ours(args):
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
+    pmdarray = None
+    if rank == 0 and world == 1 and not args.no_e2e:
+        # BASELINE.json configs[4]: PMDArray reconstruction (CSR U . R diag(s) Vt, un-normalised) on this decomposition:
+        # full frames and a cropped slice, host ndarray out (the device->host copy of the frames is inside the timing)
+        arr_r = localmd_b200.localmd_decomposition(movie, **kw)
+        n_fr = 256
+        pmdarray = {}
+        for name_r, key_r in (("full_frames", (slice(1000, 1000 + n_fr),)),
+                              ("crop_128x128", (slice(1000, 1000 + n_fr), slice(100, 228), slice(300, 428)))):
+            arr_r[key_r]  # warm-up (device state, library handles)
+            torch.cuda.synchronize(dev)
+            t_r = time.perf_counter()
+            out_r = arr_r[key_r]
+            dt_r = time.perf_counter() - t_r
+            pmdarray[name_r] = {"frames_per_s": n_fr / dt_r, "ms": dt_r * 1e3, "out_MB": out_r.nbytes / 1e6}
+        del arr_r, out_r
     launches = ops.LAUNCHES["count"] - n0
     if world > 1:
         tms_t = torch.tensor([ms], device=dev)
@@ -343,7 +359,7 @@ def run_ours(args):
         "metric": "frames/sec compressed", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, world), "clocks": clocks,
-        "gpu_launches": launches, "roofline": roofline, "e2e": e2e,
+        "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "pmdarray_reconstruction": pmdarray,
         "stage_ms": {k: round(float(np.mean([p[k] for p in per_step])), 3) for k in per_step[0]
                      if isinstance(per_step[0][k], float) and "." not in k},
     }

@@ -169,7 +169,7 @@ class PMDArray:
         implied = used.shape
         out = self.reconstruct(frames, used.reshape(-1))
         out = out.reshape((len(frames),) + implied)
-        return out.squeeze().astype(self.dtype)
+        return out.squeeze().astype(self.dtype, copy=False)
 
     def reconstruct(self, frames, pix, max_bytes=1 << 30):
         """(len(frames), len(pix)) float32 host array of reconstructed values at physical pixels `pix`."""
@@ -177,11 +177,14 @@ class PMDArray:
         dev = st["device"]
         pix_t = torch.from_numpy(np.ascontiguousarray(pix, dtype=np.int32)).to(dev)
         frames = np.asarray(frames, dtype=np.int64)
-        out = np.empty((len(frames), len(pix)), dtype=np.float32)
+        # the result lands in a page-locked buffer from torch's caching host allocator (copies at PCIe rate, overlapped
+        # with the reconstruction of the next chunk); the returned ndarray is a view that keeps the buffer alive
+        out_t = torch.empty((len(frames), len(pix)), dtype=torch.float32, pin_memory=True)
         step = max(4, int(max_bytes // max(4 * len(pix), 1)) // 4 * 4)
         for s0 in range(0, len(frames), step):
             fr = torch.from_numpy(frames[s0 : s0 + step]).to(dev)
             c = torch.matmul(st["rs"], st["vt"].index_select(1, fr)).contiguous()  # (R_total, n)
             chunk = ops.reconstruct(st["indptr"], st["indices"], st["values"], c, pix_t, st["std"], st["mean"])
-            out[s0 : s0 + step] = chunk.cpu().numpy()
-        return out
+            out_t[s0 : s0 + step].copy_(chunk, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        return out_t.numpy()

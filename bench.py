@@ -190,6 +190,12 @@ def workload_config(name, n_gpus):
 
 
 def run_ours(args):
+    # stdout must carry exactly ONE JSON line, but libraries print there too (NCCL writes its version banner to file
+    # descriptor 1 at communicator creation): descriptor 1 is pointed at stderr for the whole run and the JSON line is
+    # written to the saved descriptor at the end
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
 
     import localmd_b200
@@ -206,8 +212,6 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
-        # NCCL_DEBUG=VERSION/INFO makes NCCL print to stdout, which must carry exactly one JSON line
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
         group = dist.group.WORLD
     w = WORKLOADS[args.workload]
@@ -367,7 +371,8 @@ def run_ours(args):
         scaled, raw, sample, cores, _ = cpu_reference_sample(w)
         line["cpu_baseline"] = {"value": scaled, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
                                 "sample_frames_per_s": raw}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":

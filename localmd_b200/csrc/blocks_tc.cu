@@ -72,6 +72,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "}\n" ::"r"(bar), "r"(parity));
 }
 
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "elect.sync _|P1, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
 }
@@ -245,23 +256,39 @@ block_project_tc_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld,
                 }
             }
         }
-    } else if (lane == 0) {
-        // ================================ MMA issuer (one thread) ================================
+    } else {
+        // ================================ MMA issuer ================================
+        // the whole warp runs the (uniform) loop so that addresses and descriptors stay in uniform registers; one
+        // elected lane issues the MMAs and the commit of a stage
+        // MN-major SWIZZLE_128B_BASE32B descriptor: low word = start address >> 4 | LBO << 16, high word = SBO | version | type
+        constexpr uint64_t desc_hi = (uint64_t)((512u >> 4) | (1u << 14) | (1u << 29)) << 32;
+        constexpr uint32_t lbo = (uint32_t)(kTCGroupStride >> 4) << 16;
+        const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+        const bool leader = tc_elect_one();
+        int st = 0;
+        uint32_t par = 0;
         for (int ch = 0; ch < nch; ++ch) {
-            const int st = ch % kTCStages;
-            mbar_wait(smem_u32(&bar_full[st]), (ch / kTCStages) & 1);
+            mbar_wait(full0 + 8 * st, par);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
-            const uint32_t a0 = sbase + st * kTCStageBytes, b_hi = a0 + 2 * kTCTiles * kTCABytes, b_lo = b_hi + kTCBBytes;
-            const uint64_t dbh = umma_desc(b_hi), dbl = umma_desc(b_lo);
+            if (leader) {
+                const uint32_t a0 = ((sbase + st * kTCStageBytes) >> 4) | lbo;
+                const uint32_t b_hi = a0 + ((2 * kTCTiles * kTCABytes) >> 4), b_lo = b_hi + (kTCBBytes >> 4);
+                const uint64_t dbh = desc_hi | b_hi, dbl = desc_hi | b_lo;
 #pragma unroll
-            for (int tl = 0; tl < kTCTiles; ++tl) {
-                const uint64_t dah = umma_desc(a0 + tl * 2 * kTCABytes), dal = umma_desc(a0 + tl * 2 * kTCABytes + kTCABytes);
-                umma_tf32(tmem_d + kTCN * tl, dah, dbl, idesc, ch != 0);
-                umma_tf32(tmem_d + kTCN * tl, dal, dbh, idesc, 1u);
-                umma_tf32(tmem_d + kTCN * tl, dah, dbh, idesc, 1u);
+                for (int tl = 0; tl < kTCTiles; ++tl) {
+                    const uint64_t dah = desc_hi | (a0 + ((tl * 2 * kTCABytes) >> 4));
+                    const uint64_t dal = dah + (kTCABytes >> 4);
+                    umma_tf32(tmem_d + kTCN * tl, dah, dbl, idesc, ch != 0);
+                    umma_tf32(tmem_d + kTCN * tl, dal, dbh, idesc, 1u);
+                    umma_tf32(tmem_d + kTCN * tl, dah, dbh, idesc, 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(empty0 + 8 * st)
+                             : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar_empty[st]))
-                         : "memory");
+            if (++st == kTCStages) {
+                st = 0;
+                par ^= 1;
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
@@ -455,28 +482,34 @@ block_spatial_tc_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld,
                 }
             }
         }
-    } else if (lane == 0) {
+    } else {
         // ================================ MMA issuer ================================
+        // whole warp, uniform control flow; one elected lane issues (see block_project_tc_kernel)
+        constexpr uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;   // K-major SWIZZLE_128B
+        const uint32_t full0 = smem_u32(&bar_full[0]), empty0 = smem_u32(&bar_empty[0]);
+        const bool leader = tc_elect_one();
         for (int ch = 0; ch < nch; ++ch) {
             const int st = ch & 1;
-            mbar_wait(smem_u32(&bar_full[st]), (ch >> 1) & 1);
+            mbar_wait(full0 + 8 * st, (ch >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
-            const uint32_t base = sbase + st * kSTStageBytes;
-            const uint32_t b_hi = base + 2 * kSTTiles * kSTABytes, b_lo = b_hi + kSTBBytes;
+            if (leader) {
+                const uint32_t base = (sbase + st * kSTStageBytes) >> 4;
+                const uint32_t b_hi = base + ((2 * kSTTiles * kSTABytes) >> 4), b_lo = b_hi + (kSTBBytes >> 4);
 #pragma unroll
-            for (int ks = 0; ks < kSTK / 8; ++ks) {
-                const uint64_t dbh = umma_desc_k(b_hi + 32 * ks), dbl = umma_desc_k(b_lo + 32 * ks);
+                for (int ks = 0; ks < kSTK / 8; ++ks) {
+                    const uint64_t dbh = desc_hi | (b_hi + 2 * ks), dbl = desc_hi | (b_lo + 2 * ks);
 #pragma unroll
-                for (int tl = 0; tl < kSTTiles; ++tl) {
-                    const uint32_t a_hi = base + tl * 2 * kSTABytes, a_lo = a_hi + kSTABytes;
-                    const uint64_t dah = umma_desc_k(a_hi + 32 * ks), dal = umma_desc_k(a_lo + 32 * ks);
-                    umma_tf32(tmem_d + 64 * tl, dah, dbl, idesc, (ch | ks) != 0);
-                    umma_tf32(tmem_d + 64 * tl, dal, dbh, idesc, 1u);
-                    umma_tf32(tmem_d + 64 * tl, dah, dbh, idesc, 1u);
+                    for (int tl = 0; tl < kSTTiles; ++tl) {
+                        const uint32_t a_hi = base + ((tl * 2 * kSTABytes) >> 4), a_lo = a_hi + (kSTABytes >> 4);
+                        const uint64_t dah = desc_hi | (a_hi + 2 * ks), dal = desc_hi | (a_lo + 2 * ks);
+                        umma_tf32(tmem_d + 64 * tl, dah, dbl, idesc, (ch | ks) != 0);
+                        umma_tf32(tmem_d + 64 * tl, dal, dbh, idesc, 1u);
+                        umma_tf32(tmem_d + 64 * tl, dah, dbh, idesc, 1u);
+                    }
                 }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(empty0 + 8 * st)
+                             : "memory");
             }
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&bar_empty[st]))
-                         : "memory");
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::);

@@ -482,10 +482,11 @@ class SparseU:
         self._csr = None
         self.supertiles = None
         self.strips = None
-        rows = sorted(set(int(x) for x in starts[:, 0])) if len(ranks_host) else []
-        cols = sorted(set(int(x) for x in starts[:, 1])) if len(ranks_host) else []
+        st64 = np.asarray(starts, dtype=np.int64).reshape(-1, 2)
+        rows = np.unique(st64[:, 0]).tolist() if len(ranks_host) else []
+        cols = np.unique(st64[:, 1]).tolist() if len(ranks_host) else []
         regular = len(ranks_host) > 0 and len(rows) * len(cols) == len(ranks_host) and np.array_equal(
-            np.asarray(starts, dtype=np.int64), np.array([(a, c) for a in rows for c in cols], dtype=np.int64))
+            st64, np.stack(np.meshgrid(rows, cols, indexing="ij"), axis=-1).reshape(-1, 2))
         self.strips_tc = None
         self._regular = (rows, cols) if regular else None
         self._tc_thread = None
@@ -934,7 +935,7 @@ def localmd_decomposition(
         tm.mark("init_filter")
 
         dim_1_iters, dim_2_iters = tile_starts(d1, bh), tile_starts(d2, bw)
-        starts = np.array([(k, j) for k in dim_1_iters for j in dim_2_iters], dtype=np.int32)
+        starts = np.stack(np.meshgrid(dim_1_iters, dim_2_iters, indexing="ij"), axis=-1).reshape(-1, 2).astype(np.int32)
         nb = starts.shape[0]
         starts_dev = torch.from_numpy(starts).to(dev)
         block_weights = pyramid_weights(bh, bw)

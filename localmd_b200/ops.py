@@ -391,8 +391,13 @@ def project_cols_f64(w64, d2, starts, bh, bw, blk_of_col, col0, uvals64, bg64):
     n_local = uvals64.shape[0]
     n_cols = n_local + bg64.shape[0]
     z = torch.empty((n_cols, m), dtype=torch.float64, device=w64.device)
-    _call("pmd_project_cols_f64", _p(w64), m, d2, d, _p(starts), bh, bw, _p(blk_of_col), _p(col0), n_local, _p(uvals64),
-          _p(bg64), n_cols, _p(z), _stream())
+    # the kernel gives one warp to every column: right for the block-supported columns (b pixels each), but a dense
+    # background column walks all d pixels -- those K rows are a plain (K x d)(d x m) library GEMM instead
+    if n_local > 0:
+        _call("pmd_project_cols_f64", _p(w64), m, d2, d, _p(starts), bh, bw, _p(blk_of_col), _p(col0), n_local, _p(uvals64),
+              _p(bg64), n_local, _p(z), _stream())
+    if n_cols > n_local:
+        torch.matmul(bg64, w64.t(), out=z[n_local:])
     return z
 
 

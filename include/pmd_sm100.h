@@ -92,6 +92,17 @@ int pmd_standardize_frames_t(const void* movie, int dtype, int64_t d, const int6
 int pmd_block_orth(float* x, int64_t batch, int64_t m, int64_t n, int64_t ldx, const double* g_ext,
                    int64_t passes, void* stream);
 
+/* Background removal on the pixel-major init movie yt [d][ld] (ld a multiple of 4, padding columns included):
+ *   pmd_bg_project_t: part[g][c][f] = sum over the pixels of range g of bg[c][p] * yt[p][f]   (n_ranges equal pixel
+ *                     ranges; the caller sums the partials over g in a fixed order -> vbg [k][ld], deterministic)
+ *   pmd_bg_remove_t:  yt[p][f] -= sum_c bg[c][p] * vbg[c][f]
+ * bg: [k][d] float32 orthonormal background rows, 1 <= k <= 16.
+ * replaces: pmd_loader.py:386-387 (standardize_and_filter: temporal projection onto the spatial background basis
+ *           and its subtraction) on the init frames. */
+int pmd_bg_project_t(const float* yt, int64_t ld, int64_t d, const float* bg, int64_t k, int64_t n_ranges, float* part,
+                     void* stream);
+int pmd_bg_remove_t(float* yt, int64_t ld, int64_t d, const float* bg, int64_t k, const float* vbg, void* stream);
+
 /* 2x2(-ish) average pooling + temporal averaging of every block of the standardised init movie.
  * replaces: decomposition.py:192-232 (downsample_average_pooling) + 283-290.
  * yt: pixel-major init movie [d][ld] float32 (frame f of pixel p at yt[p*ld+f]), t frames used.

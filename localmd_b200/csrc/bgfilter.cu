@@ -1,0 +1,134 @@
+// Background removal on the pixel-major init movie (pmd_loader.py:374-389: standardize_and_filter):
+//     vbg[k][f] = sum_p bg[k][p] * yt[p][f]          (K <= 16 dense background components)
+//     yt[p][f] -= sum_k bg[k][p] * vbg[k][f]
+// Both are skinny contractions (K = 15 at the defaults) bound by one pass over yt (5.2 GB at C2); the library GEMMs
+// picked for these shapes take 2-3x the streaming time.  A thread owns 4 consecutive frames and keeps its K x 4
+// accumulators (pass 1) or its K x 4 slice of vbg (pass 2) in registers while it walks a range of pixels; the K
+// coefficients of a pixel are broadcast from shared memory.  Pass 1 writes one partial per pixel range (summed in a
+// fixed order by the caller: deterministic, no atomics).
+#include "common.cuh"
+
+namespace pmd {
+
+constexpr int kBGK = 16;
+constexpr int kBGThreads = 256;
+constexpr int kBGPix = 256;   // pixels staged per shared-memory refill
+constexpr int kBGBatch = 8;   // pixel rows loaded before they are consumed (memory-level parallelism)
+
+// part[g][k][f] = sum over the pixels of range g
+__global__ void __launch_bounds__(kBGThreads)
+bg_project_t_kernel(const float* __restrict__ yt, int64_t ld, int64_t d, const float* __restrict__ bg, int k_n, int64_t pix_per_cta,
+                    float* __restrict__ part) {
+    __shared__ float sb[kBGK][kBGPix];
+    const int64_t f = ((int64_t)blockIdx.x * kBGThreads + threadIdx.x) * 4;
+    const int64_t p0 = (int64_t)blockIdx.y * pix_per_cta, p1 = min(d, p0 + pix_per_cta);
+    float4 acc[kBGK];
+#pragma unroll
+    for (int k = 0; k < kBGK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t pb = p0; pb < p1; pb += kBGPix) {
+        const int n = (int)min((int64_t)kBGPix, p1 - pb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kBGK * kBGPix; i += kBGThreads) {
+            const int k = i / kBGPix, q = i - k * kBGPix;
+            sb[k][q] = (k < k_n && q < n) ? bg[(int64_t)k * d + pb + q] : 0.f;
+        }
+        __syncthreads();
+        if (f < ld) {
+            const float* src = yt + pb * ld + f;
+            for (int q0 = 0; q0 < n; q0 += kBGBatch) {   // kBGBatch independent 128-bit loads in flight per thread
+                float4 y[kBGBatch];
+#pragma unroll
+                for (int j = 0; j < kBGBatch; ++j)
+                    y[j] = q0 + j < n ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)(q0 + j) * ld)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int j = 0; j < kBGBatch; ++j) {
+#pragma unroll
+                    for (int k = 0; k < kBGK; ++k) {
+                        const float b = sb[k][min(q0 + j, kBGPix - 1)];
+                        acc[k].x = fmaf(b, y[j].x, acc[k].x);
+                        acc[k].y = fmaf(b, y[j].y, acc[k].y);
+                        acc[k].z = fmaf(b, y[j].z, acc[k].z);
+                        acc[k].w = fmaf(b, y[j].w, acc[k].w);
+                    }
+                }
+            }
+        }
+    }
+    if (f < ld) {
+        float* out = part + (int64_t)blockIdx.y * k_n * ld + f;
+#pragma unroll
+        for (int k = 0; k < kBGK; ++k)
+            if (k < k_n) *reinterpret_cast<float4*>(out + (int64_t)k * ld) = acc[k];
+    }
+}
+
+__global__ void __launch_bounds__(kBGThreads)
+bg_remove_t_kernel(float* __restrict__ yt, int64_t ld, int64_t d, const float* __restrict__ bg, int k_n, const float* __restrict__ vbg,
+                   int64_t pix_per_cta) {
+    __shared__ float sb[kBGK][kBGPix];
+    const int64_t f = ((int64_t)blockIdx.x * kBGThreads + threadIdx.x) * 4;
+    const int64_t p0 = (int64_t)blockIdx.y * pix_per_cta, p1 = min(d, p0 + pix_per_cta);
+    float4 v[kBGK];
+#pragma unroll
+    for (int k = 0; k < kBGK; ++k)
+        v[k] = (k < k_n && f < ld) ? *reinterpret_cast<const float4*>(vbg + (int64_t)k * ld + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t pb = p0; pb < p1; pb += kBGPix) {
+        const int n = (int)min((int64_t)kBGPix, p1 - pb);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kBGK * kBGPix; i += kBGThreads) {
+            const int k = i / kBGPix, q = i - k * kBGPix;
+            sb[k][q] = (k < k_n && q < n) ? bg[(int64_t)k * d + pb + q] : 0.f;
+        }
+        __syncthreads();
+        if (f < ld) {
+            float* dst = yt + pb * ld + f;
+            for (int q0 = 0; q0 < n; q0 += kBGBatch) {
+                float4 y[kBGBatch];
+#pragma unroll
+                for (int j = 0; j < kBGBatch; ++j)
+                    if (q0 + j < n) y[j] = *reinterpret_cast<const float4*>(dst + (int64_t)(q0 + j) * ld);
+#pragma unroll
+                for (int j = 0; j < kBGBatch; ++j) {
+                    if (q0 + j < n) {
+#pragma unroll
+                        for (int k = 0; k < kBGK; ++k) {
+                            const float b = -sb[k][q0 + j];
+                            y[j].x = fmaf(b, v[k].x, y[j].x);
+                            y[j].y = fmaf(b, v[k].y, y[j].y);
+                            y[j].z = fmaf(b, v[k].z, y[j].z);
+                            y[j].w = fmaf(b, v[k].w, y[j].w);
+                        }
+                        *reinterpret_cast<float4*>(dst + (int64_t)(q0 + j) * ld) = y[j];
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace pmd
+
+extern "C" int pmd_bg_project_t(const float* yt, int64_t ld, int64_t d, const float* bg, int64_t k, int64_t n_ranges, float* part,
+                                void* stream) {
+    const char* fn = "pmd_bg_project_t";
+    PMD_REQUIRE(yt && bg && part, fn, "null pointer");
+    PMD_REQUIRE(ld > 0 && ld % 4 == 0 && d > 0 && k > 0 && k <= pmd::kBGK && n_ranges > 0 && n_ranges <= 65535, fn,
+                "bad size (ld multiple of 4, 1 <= k <= 16)");
+    PMD_REQUIRE(((uintptr_t)yt % 16) == 0 && ((uintptr_t)part % 16) == 0, fn, "operands must be 16-byte aligned");
+    const int64_t per = (d + n_ranges - 1) / n_ranges;
+    dim3 grid((unsigned)((ld / 4 + pmd::kBGThreads - 1) / pmd::kBGThreads), (unsigned)n_ranges);
+    pmd::bg_project_t_kernel<<<grid, pmd::kBGThreads, 0, (cudaStream_t)stream>>>(yt, ld, d, bg, (int)k, per, part);
+    return pmd::check_launch(fn);
+}
+
+extern "C" int pmd_bg_remove_t(float* yt, int64_t ld, int64_t d, const float* bg, int64_t k, const float* vbg, void* stream) {
+    const char* fn = "pmd_bg_remove_t";
+    PMD_REQUIRE(yt && bg && vbg, fn, "null pointer");
+    PMD_REQUIRE(ld > 0 && ld % 4 == 0 && d > 0 && k > 0 && k <= pmd::kBGK, fn, "bad size (ld multiple of 4, 1 <= k <= 16)");
+    PMD_REQUIRE(((uintptr_t)yt % 16) == 0 && ((uintptr_t)vbg % 16) == 0, fn, "operands must be 16-byte aligned");
+    const int64_t n_ranges = std::min<int64_t>(1024, (d + 255) / 256);
+    const int64_t per = (d + n_ranges - 1) / n_ranges;
+    dim3 grid((unsigned)((ld / 4 + pmd::kBGThreads - 1) / pmd::kBGThreads), (unsigned)n_ranges);
+    pmd::bg_remove_t_kernel<<<grid, pmd::kBGThreads, 0, (cudaStream_t)stream>>>(yt, ld, d, bg, (int)k, vbg, per);
+    return pmd::check_launch(fn);
+}

@@ -928,8 +928,12 @@ def localmd_decomposition(
             idx = torch.arange(src2d.shape[0], dtype=torch.int64, device=dev)
         yt = ops.standardize_frames_t(src2d, idx, mean, std)  # (d, ld)
         del src2d, idx
-        vbg = torch.matmul(bg, yt).contiguous()  # (K, ld)
-        yt.addmm_(bg.t(), vbg, alpha=-1.0)
+        if bg.shape[0] <= 16:   # skinny contractions: one streaming pass over yt each (csrc/bgfilter.cu)
+            vbg = ops.bg_project_t(yt, bg)  # (K, ld)
+            ops.bg_remove_t(yt, bg, vbg)
+        else:
+            vbg = torch.matmul(bg, yt).contiguous()  # (K, ld)
+            yt.addmm_(bg.t(), vbg, alpha=-1.0)
         if pixel_weighting is not None:
             yt *= _as_dev(np.asarray(pixel_weighting, dtype=np.float32).reshape(-1), dev)[:, None]
         tm.mark("init_filter")

@@ -171,6 +171,25 @@ def standardize_frames_t(movie2d, frames, mean, stdv, ld=None):
     return out
 
 
+def bg_project_t(yt, bg, n_ranges=128):
+    """vbg (K, ld) = bg (K, d) @ yt (d, ld) for the pixel-major init movie, K <= 16 (deterministic two-stage sum)."""
+    _req(yt, torch.float32, "yt"), _req(bg, torch.float32, "bg")
+    d, ld = yt.shape
+    k = bg.shape[0]
+    n_ranges = max(1, min(int(n_ranges), (d + 255) // 256))
+    part = torch.empty((n_ranges, k, ld), dtype=torch.float32, device=yt.device)
+    _call("pmd_bg_project_t", _p(yt), ld, d, _p(bg), k, n_ranges, _p(part), _stream())
+    return part.sum(dim=0)
+
+
+def bg_remove_t(yt, bg, vbg):
+    """yt (d, ld) -= bg^T (d, K) @ vbg (K, ld), in place, K <= 16."""
+    _req(yt, torch.float32, "yt"), _req(bg, torch.float32, "bg"), _req(vbg, torch.float32, "vbg")
+    d, ld = yt.shape
+    _call("pmd_bg_remove_t", _p(yt), ld, d, _p(bg), bg.shape[0], _p(vbg), _stream())
+    return yt
+
+
 def _split_tf32(x):
     """x = hi + lo with hi exactly representable in TF32 (10 mantissa bits, round to nearest)."""
     hi = ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)

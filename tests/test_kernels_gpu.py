@@ -565,3 +565,21 @@ def test_reconstruct(ops, n):
     out2 = ops.reconstruct(dev(U32.indptr.astype(np.int64)), dev(U32.indices.astype(np.int32)), dev(U32.data), dev(c), dev(pix),
                            None, None).cpu().numpy()
     np.testing.assert_allclose(out2, (U[pix] @ c.astype(np.float64)).T, rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("d,t,K", [(300, 1000, 15), (1030, 37 * 4, 1), (257, 1028, 16), (64, 8, 3)])
+def test_bg_filter_t(ops, d, t, K):
+    """Background projection / removal on the pixel-major init movie (csrc/bgfilter.cu) against float64 matmuls."""
+    rng = np.random.default_rng(d + K)
+    ld = (t + 3) // 4 * 4
+    yt = np.zeros((d, ld), np.float32)
+    yt[:, :t] = rng.standard_normal((d, t)).astype(np.float32)
+    bg = np.linalg.qr(rng.standard_normal((d, K)))[0].T.astype(np.float32)
+    ytd, bgd = dev(yt), dev(bg)
+    vbg = ops.bg_project_t(ytd, bgd, n_ranges=7)
+    ref_v = bg.astype(np.float64) @ yt.astype(np.float64)
+    np.testing.assert_allclose(vbg.cpu().numpy(), ref_v, rtol=0, atol=2e-5 * np.abs(ref_v).max())
+    ops.bg_remove_t(ytd, bgd, vbg)
+    ref_y = yt.astype(np.float64) - bg.T.astype(np.float64) @ vbg.cpu().numpy().astype(np.float64)
+    np.testing.assert_allclose(ytd.cpu().numpy(), ref_y, rtol=0, atol=1e-5)
+    assert np.all(ytd.cpu().numpy()[:, t:] == 0)

@@ -26,32 +26,52 @@ __device__ __forceinline__ void cp_async_wait() {
 // ------------------------------------------------------------------------------------------------
 // yT[p][i] = (movie[frames[i]][p] - mean[p]) / stdv[p]     (32 x 32 transposing tiles)
 // ------------------------------------------------------------------------------------------------
+// A CTA transposes kSTTileSets = 4 neighbouring 32 x 32 tiles: a warp reads 4 x 128 contiguous bytes of the same frame back
+// to back (DRAM sees 512-byte bursts instead of isolated 128-byte lines) and has 16 independent loads in flight.
+constexpr int kSTTileSets = 4;
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 standardize_frames_t_kernel(const T* __restrict__ movie, int64_t d, const int64_t* __restrict__ frames, int64_t n,
                             const float* __restrict__ mean, const float* __restrict__ stdv, float* __restrict__ out,
                             int64_t ld) {
-    __shared__ float tile[32][33];
+    __shared__ float tile[kSTTileSets][32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int64_t p0 = (int64_t)blockIdx.x * 32, i0 = (int64_t)blockIdx.y * 32;
-    const int64_t p = p0 + tx;
-    float mu = 0.f, sd = 1.f;
-    if (p < d) {
-        mu = mean[p];
-        sd = stdv[p];
-    }
+    const int64_t p0 = (int64_t)blockIdx.x * (32 * kSTTileSets), i0 = (int64_t)blockIdx.y * 32;
+    int64_t fr[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int64_t i = i0 + ty + 8 * j;
-        float v = 0.f;
-        if (i < n && p < d) v = (to_f32(movie[frames[i] * d + p]) - mu) / sd;
-        tile[ty + 8 * j][tx] = v;
+        fr[j] = i < n ? frames[i] : -1;
+    }
+    float raw[kSTTileSets][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {      // the 4 lines of one frame are requested back to back
+#pragma unroll
+        for (int s = 0; s < kSTTileSets; ++s) {
+            const int64_t p = p0 + 32 * s + tx;
+            raw[s][j] = (fr[j] >= 0 && p < d) ? to_f32(movie[fr[j] * d + p]) : 0.f;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < kSTTileSets; ++s) {
+        const int64_t p = p0 + 32 * s + tx;
+        float mu = 0.f, sd = 1.f;
+        if (p < d) {
+            mu = mean[p];
+            sd = stdv[p];
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tile[s][ty + 8 * j][tx] = (fr[j] >= 0 && p < d) ? (raw[s][j] - mu) / sd : 0.f;
     }
     __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int64_t pp = p0 + ty + 8 * j, i = i0 + tx;
-        if (pp < d && i < ld) out[pp * ld + i] = tile[tx][ty + 8 * j];
+    for (int s = 0; s < kSTTileSets; ++s) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t pp = p0 + 32 * s + ty + 8 * j, i = i0 + tx;
+            if (pp < d && i < ld) out[pp * ld + i] = tile[s][tx][ty + 8 * j];
+        }
     }
 }
 
@@ -361,7 +381,7 @@ extern "C" int pmd_standardize_frames_t(const void* movie, int dtype, int64_t d,
     PMD_REQUIRE(d > 0 && n_frames > 0 && ld >= n_frames, fn, "bad size");
     const int64_t gy = (ld + 31) / 32;
     PMD_REQUIRE(gy <= 65535, fn, "more than 65535*32 frames per call");
-    dim3 grid((unsigned)((d + 31) / 32), (unsigned)gy);
+    dim3 grid((unsigned)((d + 32 * pmd::kSTTileSets - 1) / (32 * pmd::kSTTileSets)), (unsigned)gy);
     cudaStream_t st = (cudaStream_t)stream;
     PMD_DISPATCH_DTYPE(dtype, fn, {
         pmd::standardize_frames_t_kernel<scalar_t><<<grid, 256, 0, st>>>((const scalar_t*)movie, d, frames, n_frames, mean, stdv,

@@ -13,7 +13,7 @@ namespace pmd {
 constexpr int kBGK = 16;
 constexpr int kBGThreads = 256;
 constexpr int kBGPix = 256;   // pixels staged per shared-memory refill
-constexpr int kBGBatch = 8;   // pixel rows loaded before they are consumed (memory-level parallelism)
+constexpr int kBGBatch = 4;   // pixel rows per pipeline step of the projection (two steps in flight per thread)
 
 // part[g][k][f] = sum over the pixels of range g
 __global__ void __launch_bounds__(kBGThreads)
@@ -34,23 +34,30 @@ bg_project_t_kernel(const float* __restrict__ yt, int64_t ld, int64_t d, const f
         }
         __syncthreads();
         if (f < ld) {
+            // software pipeline: the next kBGBatch pixel rows are in flight while the current ones are consumed
             const float* src = yt + pb * ld + f;
-            for (int q0 = 0; q0 < n; q0 += kBGBatch) {   // kBGBatch independent 128-bit loads in flight per thread
-                float4 y[kBGBatch];
+            float4 cur[kBGBatch], nxt[kBGBatch];
+            auto load = [&](float4 (&y)[kBGBatch], int q0) {
 #pragma unroll
                 for (int j = 0; j < kBGBatch; ++j)
                     y[j] = q0 + j < n ? __ldg(reinterpret_cast<const float4*>(src + (int64_t)(q0 + j) * ld)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            load(cur, 0);
+            for (int q0 = 0; q0 < n; q0 += kBGBatch) {
+                load(nxt, q0 + kBGBatch);
 #pragma unroll
                 for (int j = 0; j < kBGBatch; ++j) {
 #pragma unroll
                     for (int k = 0; k < kBGK; ++k) {
                         const float b = sb[k][min(q0 + j, kBGPix - 1)];
-                        acc[k].x = fmaf(b, y[j].x, acc[k].x);
-                        acc[k].y = fmaf(b, y[j].y, acc[k].y);
-                        acc[k].z = fmaf(b, y[j].z, acc[k].z);
-                        acc[k].w = fmaf(b, y[j].w, acc[k].w);
+                        acc[k].x = fmaf(b, cur[j].x, acc[k].x);
+                        acc[k].y = fmaf(b, cur[j].y, acc[k].y);
+                        acc[k].z = fmaf(b, cur[j].z, acc[k].z);
+                        acc[k].w = fmaf(b, cur[j].w, acc[k].w);
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < kBGBatch; ++j) cur[j] = nxt[j];
             }
         }
     }
@@ -81,26 +88,34 @@ bg_remove_t_kernel(float* __restrict__ yt, int64_t ld, int64_t d, const float* _
         }
         __syncthreads();
         if (f < ld) {
+            // software pipeline as in the projection: the next rows are loaded while the current ones are updated
             float* dst = yt + pb * ld + f;
-            for (int q0 = 0; q0 < n; q0 += kBGBatch) {
-                float4 y[kBGBatch];
+            float4 cur[kBGBatch], nxt[kBGBatch];
+            auto load = [&](float4 (&y)[kBGBatch], int q0) {
 #pragma unroll
                 for (int j = 0; j < kBGBatch; ++j)
                     if (q0 + j < n) y[j] = *reinterpret_cast<const float4*>(dst + (int64_t)(q0 + j) * ld);
+            };
+            load(cur, 0);
+            for (int q0 = 0; q0 < n; q0 += kBGBatch) {
+                load(nxt, q0 + kBGBatch);
 #pragma unroll
                 for (int j = 0; j < kBGBatch; ++j) {
                     if (q0 + j < n) {
+                        float4 y = cur[j];
 #pragma unroll
                         for (int k = 0; k < kBGK; ++k) {
                             const float b = -sb[k][q0 + j];
-                            y[j].x = fmaf(b, v[k].x, y[j].x);
-                            y[j].y = fmaf(b, v[k].y, y[j].y);
-                            y[j].z = fmaf(b, v[k].z, y[j].z);
-                            y[j].w = fmaf(b, v[k].w, y[j].w);
+                            y.x = fmaf(b, v[k].x, y.x);
+                            y.y = fmaf(b, v[k].y, y.y);
+                            y.z = fmaf(b, v[k].z, y.z);
+                            y.w = fmaf(b, v[k].w, y.w);
                         }
-                        *reinterpret_cast<float4*>(dst + (int64_t)(q0 + j) * ld) = y[j];
+                        *reinterpret_cast<float4*>(dst + (int64_t)(q0 + j) * ld) = y;
                     }
                 }
+#pragma unroll
+                for (int j = 0; j < kBGBatch; ++j) cur[j] = nxt[j];
             }
         }
     }

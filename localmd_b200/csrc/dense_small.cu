@@ -99,6 +99,101 @@ gram_f64_kernel(const float* __restrict__ a, int n, int64_t m_len, int64_t bs, i
 }
 
 // ------------------------------------------------------------------------------------------------
+// The same Gram matrices on the FP64 tensor cores (mma.sync m8n8k4, DMMA), for rows that are contiguous in memory
+// (inner stride 1): C[b] += A_b[:, m0:m1] A_b[:, m0:m1]^T.  float32 inputs are exact in float64, every product is exact
+// and the accumulation is IEEE float64, as in the FMA kernel above; only the summation order differs.
+// A CTA stages [n rows][kDGK values] float32 tiles in shared memory (row pitch = 4 mod 32 words: the 8 x 4 fragment
+// loads of a warp are bank-conflict free); warp w owns the upper-triangle 8 x 8 output tiles w, w + 8, ...
+// ------------------------------------------------------------------------------------------------
+constexpr int kDGK = 64;                 // inner-dimension values per shared-memory tile
+constexpr int kDGLd = kDGK + 4;          // row pitch in floats
+constexpr int kDGThreads = 256;
+constexpr int kDGMaxTiles = 14;          // ceil(14 * 15 / 2 / 8) upper-triangle tiles per warp for n <= 112
+
+__global__ void __launch_bounds__(kDGThreads)
+gram_dmma_kernel(const float* __restrict__ a, int n, int64_t m_len, int64_t bs, int64_t rs, int64_t m_per_cta,
+                 double* __restrict__ c) {
+    extern __shared__ float dsm[];       // [8 * nt][kDGLd]
+    const int nt = (n + 7) / 8;
+    const int ntiles = nt * (nt + 1) / 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t b = blockIdx.y;
+    const float* ab = a + b * bs;
+    const int64_t m_begin = (int64_t)blockIdx.x * m_per_cta;
+    const int64_t m_end = min(m_len, m_begin + m_per_cta);
+    int ti[kDGMaxTiles], tj[kDGMaxTiles];
+    double acc[kDGMaxTiles][2];
+#pragma unroll
+    for (int k = 0; k < kDGMaxTiles; ++k) {
+        const int id = warp + 8 * k;
+        ti[k] = -1;
+        tj[k] = 0;
+        if (id < ntiles) {
+            int row = 0, rem = id;
+            while (rem >= nt - row) { rem -= nt - row; ++row; }
+            ti[k] = row;
+            tj[k] = row + rem;
+        }
+        acc[k][0] = acc[k][1] = 0.0;
+    }
+    const int fr = lane >> 2, fc = lane & 3;   // fragment element of this lane: row fr (0..7), k offset fc (0..3)
+    for (int64_t m0 = m_begin; m0 < m_end; m0 += kDGK) {
+        __syncthreads();
+        for (int idx = tid; idx < 8 * nt * (kDGK / 4); idx += kDGThreads) {
+            const int i = idx / (kDGK / 4), q = idx - i * (kDGK / 4);
+            const int64_t m = m0 + 4 * q;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n) {
+                const float* src = ab + (int64_t)i * rs + m;
+                if (m + 3 < m_end && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+                    v = __ldg(reinterpret_cast<const float4*>(src));
+                } else {
+                    if (m < m_end) v.x = src[0];
+                    if (m + 1 < m_end) v.y = src[1];
+                    if (m + 2 < m_end) v.z = src[2];
+                    if (m + 3 < m_end) v.w = src[3];
+                }
+            }
+            *reinterpret_cast<float4*>(dsm + i * kDGLd + 4 * q) = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kDGMaxTiles; ++k) {
+            if (ti[k] < 0) continue;
+            const float* pa = dsm + (8 * ti[k] + fr) * kDGLd + fc;
+            const float* pb = dsm + (8 * tj[k] + fr) * kDGLd + fc;
+            double c0 = acc[k][0], c1 = acc[k][1];
+#pragma unroll
+            for (int kk = 0; kk < kDGK; kk += 4) {
+                const double av = (double)pa[kk], bv = (double)pb[kk];
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};\n"
+                             : "+d"(c0), "+d"(c1)
+                             : "d"(av), "d"(bv));
+            }
+            acc[k][0] = c0;
+            acc[k][1] = c1;
+        }
+    }
+    // C fragment: lane holds C[fr][2 fc], C[fr][2 fc + 1] of its tile
+    double* cb = c + b * (int64_t)n * n;
+#pragma unroll
+    for (int k = 0; k < kDGMaxTiles; ++k) {
+        if (ti[k] < 0) continue;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int i = 8 * ti[k] + fr, j = 8 * tj[k] + 2 * fc + e;
+            if (i >= n || j >= n) continue;
+            if (ti[k] != tj[k]) {
+                atomicAdd(&cb[(int64_t)i * n + j], acc[k][e]);
+                atomicAdd(&cb[(int64_t)j * n + i], acc[k][e]);
+            } else {
+                atomicAdd(&cb[(int64_t)i * n + j], acc[k][e]);   // diagonal tiles hold both triangles themselves
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Batched symmetric eigensolver: parallel cyclic Jacobi (round-robin ordering), float64, one CTA per
 // matrix.  Rotations are skipped when |a_pq| <= 1e-15 sqrt(|a_pp a_qq|) (relative criterion => small
 // eigenvalues of positive definite matrices are found to high relative accuracy); the sweep loop
@@ -232,6 +327,17 @@ extern "C" int pmd_gram_f64(const float* a, int64_t batch, int64_t n, int64_t m_
     int64_t m_per = (m_len + splits - 1) / splits;
     m_per = (m_per + pmd::kGramMT - 1) / pmd::kGramMT * pmd::kGramMT;
     splits = (m_len + m_per - 1) / m_per;
+    if (inner_stride == 1 && (row_stride % 4) == 0) {
+        // contiguous rows: FP64 tensor cores
+        const int nt8 = (int)(n + 7) / 8;
+        const size_t smem_d = (size_t)8 * nt8 * pmd::kDGLd * sizeof(float);
+        cudaError_t e2 = cudaFuncSetAttribute(pmd::gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
+        if (e2 != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e2)); return (int)e2; }
+        dim3 grid_d((unsigned)splits, (unsigned)batch);
+        pmd::gram_dmma_kernel<<<grid_d, pmd::kDGThreads, smem_d, (cudaStream_t)stream>>>(a, (int)n, m_len, batch_stride, row_stride,
+                                                                                      m_per, c);
+        return pmd::check_launch(fn);
+    }
     const int nt = (int)(n + 1) / 2;
     const size_t smem = (size_t)2 * nt * (pmd::kGramMT + 1) * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(pmd::gram_f64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -202,11 +202,13 @@ def background_basis(movie: DeviceMovie, mean, std, bg_frames, bg_sketch, backgr
     return u.t().contiguous()
 
 
-def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, chunk=50):
+def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, chunk=None):
     """decomposition.py:147-189: roughness statistics of the rank-1 rSVD of pure-noise blocks.
     Every simulated block is its own tiny pixel-major movie (b, ld) for the block kernels."""
     b = bh * bw
     ld = (t_win + 3) // 4 * 4
+    if chunk is None:   # as many simulated blocks per batch as ~3 GB of noise allow (all 250 at C2: fewer, larger launches)
+        chunk = int(max(10, min(iters, (3 << 30) // (4 * b * ld))))
     starts = torch.zeros((chunk, 2), dtype=torch.int32, device=device)
     sp, tp = [], []
     have_noise = getattr(draws, "sim_noise", None) is not None

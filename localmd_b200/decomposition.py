@@ -15,7 +15,6 @@ import datetime
 import math
 import os
 import sys
-import threading
 from typing import Callable, Optional
 
 import numpy as np
@@ -491,25 +490,14 @@ class SparseU:
             st64, np.stack(np.meshgrid(rows, cols, indexing="ij"), axis=-1).reshape(-1, 2))
         self.strips_tc = None
         self._regular = (rows, cols) if regular else None
-        self._tc_thread = None
+        self._tc_host = None
         if regular and os.environ.get("PMD_K7", "tc") != "simt":
-            # K7 on the tensor cores (csrc/project_tc.cu): the host tables are built on a side thread (pure host work in
-            # the native library, the GIL is released) while the GPU runs the whitening stage; the first projection call
-            # joins it, uploads the tables and builds the coefficient images
-            def build_tables():
-                try:
-                    self._tc_host = ops.make_strips_tc(rows, cols, bh, bw, d1, d2, ranks_host, self.col0_host, bg.shape[0])
-                except BaseException as exc:  # re-raised by the thread that joins
-                    self._tc_error = exc
-
-            self._tc_error = None
-
-            self._tc_host = None
-            self._tc_thread = threading.Thread(target=build_tables)
-            self._tc_thread.start()
-        elif regular:
+            # K7 on the tensor cores (csrc/project_tc.cu): host tables now (native library), device tables and
+            # coefficient images at the first projection call
+            self._tc_host = ops.make_strips_tc(rows, cols, bh, bw, d1, d2, ranks_host, self.col0_host, bg.shape[0])
+        if regular and self._tc_host is None:
             self._build_simt_strips()
-        if self.strips is None and self._tc_thread is None:
+        if self.strips is None and self._tc_host is None:
             self._build_supertiles()
 
     def _build_supertiles(self):
@@ -523,23 +511,14 @@ class SparseU:
                                    for k, v in st.items()}
 
     def _finish_tc(self):
-        """Join the table builder; upload the tables and build the coefficient images (once)."""
-        if self._tc_thread is None:
-            return
-        self._tc_thread.join()
-        self._tc_thread = None
-        if self._tc_error is not None:
-            raise self._tc_error
+        """Upload the tensor-core tables and build the coefficient images (once, at the first projection call)."""
         st = self._tc_host
+        if st is None:
+            return
         self._tc_host = None
-        if st is not None:
-            dev = self.ranks_dev.device
-            self.strips_tc = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
-            self.bimg = ops.pack_strips_tc(self.strips_tc, self.uvals32, self.bg, self.bh * self.bw, self.d2)
-        elif self._regular is not None:
-            self._build_simt_strips()
-            if self.strips is None:
-                self._build_supertiles()
+        dev = self.ranks_dev.device
+        self.strips_tc = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+        self.bimg = ops.pack_strips_tc(self.strips_tc, self.uvals32, self.bg, self.bh * self.bw, self.d2)
 
     def _build_simt_strips(self):
         """Tables of the SIMT strip-streaming kernel (fallback of the tensor-core path: unaligned movies, tiny FOVs)."""

@@ -733,8 +733,9 @@ def projected_svd(projection, data, group=None):
         sing = torch.sqrt(vals).to(torch.float32)
         left = left.to(torch.float32)
         div = torch.where(sing == 0, torch.ones_like(sing), sing)
-        right = torch.matmul(left.t(), data) / div[:, None]
-        return torch.matmul(projection, left), sing, right
+        # the two large float32 GEMMs of the stage run on the tensor cores at float32 accuracy (3xTF32)
+        right = ops.matmul_3xtf32_any(left.t(), data) / div[:, None]
+        return ops.matmul_3xtf32_any(projection, left), sing, right
     if group is not None:
         raise NotImplementedError("frame-sharded projected_svd needs k <= T")
     d64 = data.to(torch.float64)

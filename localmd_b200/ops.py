@@ -213,6 +213,26 @@ def matmul_3xtf32(a, b):
     return out
 
 
+def matmul_3xtf32_any(a, b):
+    """matmul_3xtf32 for arbitrary shapes: every dimension is zero padded to a multiple of 8 (the TF32 tensor-core
+    kernels want 16-byte aligned rows), the result is sliced back."""
+    m, k = a.shape
+    k2, n = b.shape
+    assert k == k2
+    mp, kp, np_ = (m + 7) // 8 * 8, (k + 7) // 8 * 8, (n + 7) // 8 * 8
+    if (mp, kp) != (m, k):
+        ap = torch.zeros((mp, kp), dtype=torch.float32, device=a.device)
+        ap[:m, :k] = a
+    else:
+        ap = a
+    if (kp, np_) != (k, n):
+        bp = torch.zeros((kp, np_), dtype=torch.float32, device=b.device)
+        bp[:k, :n] = b
+    else:
+        bp = b
+    return matmul_3xtf32(ap, bp)[:m, :n]
+
+
 def block_orth_fits(m, n):
     """True when an (m, n) matrix (+ its float64 Gram) fits the shared memory of pmd_block_orth."""
     return n <= 64 and (n * (n | 1) + 2 * n) * 8 + m * (n | 1) * 4 <= 227 * 1024

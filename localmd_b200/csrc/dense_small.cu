@@ -260,13 +260,14 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
             }
             __syncthreads();
             // column rotations of A and V:  col_p <- c col_p - s col_q,  col_q <- s col_p + c col_q
-            // (thread = pair slot tid / 8, rows tid % 8, +8, ...: no integer divisions in the hot loop)
-            for (int k = tid >> 3; k < half; k += kJacThreads >> 3) {
+            // (one pair per warp, lanes along the rows: with the odd row pitch the 32 lanes of a request fall into
+            // distinct banks, where four pairs per warp collided at data-dependent offsets)
+            for (int k = tid >> 5; k < half; k += kJacThreads >> 5) {
                 const int p = pp[k];
                 if (p < 0) continue;
                 const int q = qq[k];
                 const S c = cc[k], s = ss[k];
-                for (int i = tid & 7; i < n; i += 8) {
+                for (int i = tid & 31; i < n; i += 32) {
                     const S aip = A[i * ld + p], aiq = A[i * ld + q];
                     A[i * ld + p] = c * aip - s * aiq;
                     A[i * ld + q] = s * aip + c * aiq;
@@ -277,12 +278,12 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
             }
             __syncthreads();
             // row rotations of A
-            for (int k = tid >> 3; k < half; k += kJacThreads >> 3) {
+            for (int k = tid >> 5; k < half; k += kJacThreads >> 5) {
                 const int p = pp[k];
                 if (p < 0) continue;
                 const int q = qq[k];
                 const S c = cc[k], s = ss[k];
-                for (int j = tid & 7; j < n; j += 8) {
+                for (int j = tid & 31; j < n; j += 32) {
                     const S apj = A[p * ld + j], aqj = A[q * ld + j];
                     A[p * ld + j] = c * apj - s * aqj;
                     A[q * ld + j] = s * apj + c * aqj;

@@ -147,17 +147,39 @@ extern "C" int pmd_make_strips_tc(const int32_t* row_starts, int64_t nbr, const 
     std::vector<TItem> best, cur;
     long best_cost = -1, cost = 0;
     int best_g = 0;
-    const int g_lo = g_fixed > 0 ? (int)g_fixed : 1, g_hi = g_fixed > 0 ? (int)g_fixed : 16;
+    // The cost falls with the strip width (fewer halo columns) until the live tasks overflow the slots (extra passes):
+    // the optimum sits near g* = free slots / (live block rows x tasks per block); widths in [g*/2, 2 g*] are tried.
+    int g_lo = 1, g_hi = (int)std::min<int64_t>(nbc, 64);
+    if (g_fixed > 0) {
+        g_lo = g_hi = (int)g_fixed;
+    } else {
+        double tasks = 0;
+        for (int64_t i = 0; i < nbr * nbc; ++i) tasks += (double)((ranks[i] + kSlotCols - 1) / kSlotCols);
+        const double per_block = std::max(1.0, tasks / (double)(nbr * nbc));
+        const double live_rows = (double)bh / (double)std::max<int64_t>(1, nbr > 1 ? row_starts[1] - row_starts[0] : bh);
+        const double free_slots = kSlots - (double)((n_bg + kSlotCols - 1) / kSlotCols);
+        const int g_est = std::max(1, (int)(free_slots / (live_rows * per_block)));
+        g_lo = std::max(1, g_est / 2);
+        g_hi = std::min(g_hi, 2 * g_est + 1);
+    }
     for (int g = g_lo; g <= g_hi; ++g) {
         if (!build(g, row_starts, (int)nbr, col_starts, (int)nbc, (int)bh, (int)bw, (int)d1, (int)d2, ranks, col0, (int)n_bg, cur,
                    cost))
-            break;
+            break;   // wider strips do not fit the kernel either
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             best_g = g;
             best.swap(cur);
         }
-        if (g >= nbc) break;
+    }
+    if (best_cost < 0 && g_fixed <= 0) {   // nothing in the window fitted (very wide blocks): fall back to the narrowest strips
+        for (int g = g_lo - 1; g >= 1 && best_cost < 0; --g)
+            if (build(g, row_starts, (int)nbr, col_starts, (int)nbc, (int)bh, (int)bw, (int)d1, (int)d2, ranks, col0, (int)n_bg, cur,
+                      cost)) {
+                best_cost = cost;
+                best_g = g;
+                best.swap(cur);
+            }
     }
     if (best_cost < 0) return 0;
     // largest items first: the grid is scheduled in item order, so the short row-range items fill the tail of the last wave

@@ -440,9 +440,23 @@ def project_cols_f64(w64, d2, starts, bh, bw, blk_of_col, col0, uvals64, bg64):
     return z
 
 
+_pairs_cache = {}
+
+
 def overlap_pairs(starts, bh, bw):
-    """All ordered pairs (b1, b2) of blocks whose windows intersect, sorted by (b1, b2).  Host logic."""
+    """All ordered pairs (b1, b2) of blocks whose windows intersect, sorted by (b1, b2).  Host logic; the result
+    depends on the block grid only and is memoised (a warm process decomposes many movies of one geometry)."""
     starts = np.asarray(starts, dtype=np.int64).reshape(-1, 2)
+    key = (int(bh), int(bw), starts.tobytes())
+    hit = _pairs_cache.get(key)
+    if hit is None:
+        if len(_pairs_cache) > 8:
+            _pairs_cache.clear()
+        hit = _pairs_cache[key] = _overlap_pairs(starts, bh, bw)
+    return hit
+
+
+def _overlap_pairs(starts, bh, bw):
     nb = starts.shape[0]
     rows, cols = np.unique(starts[:, 0]), np.unique(starts[:, 1])
     if len(rows) * len(cols) == nb and np.array_equal(

@@ -557,18 +557,30 @@ class SparseU:
 
     def csr(self, row_ids=None):
         """CSR arrays (indptr int64, indices int32, values float64) with rows relabelled by `row_ids`
-        (tensor mapping physical pixel -> row id; None = physical order), canonical (sorted)."""
-        rows, cols, vals = self.coo_physical()
-        if row_ids is not None:
-            rows = row_ids[rows]
-        key = rows * self.n_cols + cols
-        order = torch.argsort(key)
-        rows, cols, vals = rows[order], cols[order], vals[order]
+        (tensor mapping physical pixel -> row id, a permutation; None = physical order), canonical (sorted).
+        The physical-order form is sorted once and cached; a relabelled form is a permutation of its row segments
+        (every segment is already sorted by column), built by one scatter instead of a second sort."""
         d = self.d1 * self.d2
-        counts = torch.bincount(rows, minlength=d)
-        indptr = torch.zeros(d + 1, dtype=torch.int64, device=rows.device)
-        indptr[1:] = torch.cumsum(counts, 0)
-        return indptr, cols.to(torch.int32), vals
+        if getattr(self, "_csr64", None) is None:
+            rows, cols, vals = self.coo_physical()
+            order = torch.argsort(rows * self.n_cols + cols)
+            rows, cols, vals = rows[order], cols[order], vals[order]
+            counts = torch.bincount(rows, minlength=d)
+            indptr = torch.zeros(d + 1, dtype=torch.int64, device=rows.device)
+            indptr[1:] = torch.cumsum(counts, 0)
+            self._csr64 = (indptr, cols.to(torch.int32), vals, rows, counts)
+        indptr, cols32, vals, rows, counts = self._csr64
+        if row_ids is None:
+            return indptr, cols32, vals
+        counts_new = torch.zeros_like(counts)
+        counts_new[row_ids] = counts
+        indptr_new = torch.zeros(d + 1, dtype=torch.int64, device=rows.device)
+        indptr_new[1:] = torch.cumsum(counts_new, 0)
+        pos = indptr_new[row_ids[rows]] + (torch.arange(rows.numel(), device=rows.device) - indptr[rows])
+        cols_new, vals_new = torch.empty_like(cols32), torch.empty_like(vals)
+        cols_new[pos] = cols32
+        vals_new[pos] = vals
+        return indptr_new, cols_new, vals_new
 
     def gram(self):
         """U^T U in float64 as (CSR of the local x local part, C = U^T bg^T (n_cols, K)): the two sparse products

@@ -78,39 +78,178 @@ class lazy_data_loader(ABC):
         pass
 
 
-class TiffArray(lazy_data_loader):
-    """Placeholder with the reference's name (dataset.py:131-181).  Multipage-TIFF decoding is host
-    file I/O outside the accelerated path and needs `tifffile`, which this image does not ship."""
+class _PlainTiff:
+    """Minimal reader of uncompressed greyscale multi-page TIFF / BigTIFF files (what acquisition software, ImageJ and
+    the reference's demo data write): one image file directory per frame, or ImageJ's single directory followed by
+    `images=N` contiguous frames.  Used when the `tifffile` package is not installed; anything it does not understand
+    (compression, tiles, colour) raises ValueError naming the tag."""
+
+    _TYPES = {1: "B", 2: "c", 3: "H", 4: "I", 5: "II", 6: "b", 8: "h", 9: "i", 11: "f", 12: "d", 16: "Q", 17: "q"}
 
     def __init__(self, filename):
-        try:
-            import tifffile  # noqa: F401
-        except ImportError as e:  # pragma: no cover
-            raise ImportError("TiffArray needs the `tifffile` package, which is not installed") from e
-        import tifffile
+        import struct
 
         self.filename = filename
+        with open(filename, "rb") as f:
+            head = f.read(16)
+            if head[:2] == b"II":
+                self.bo = "<"
+            elif head[:2] == b"MM":
+                self.bo = ">"
+            else:
+                raise ValueError("%s is not a TIFF file" % filename)
+            magic = struct.unpack(self.bo + "H", head[2:4])[0]
+            if magic == 42:
+                self.big = False
+                offset = struct.unpack(self.bo + "I", head[4:8])[0]
+            elif magic == 43:
+                self.big = True
+                offset = struct.unpack(self.bo + "Q", head[8:16])[0]
+            else:
+                raise ValueError("%s is not a TIFF file (magic %d)" % (filename, magic))
+            self.pages = []
+            seen = set()
+            while offset and offset not in seen:
+                seen.add(offset)
+                tags, offset = self._read_ifd(f, offset, struct)
+                self.pages.append(self._page(tags))
+        if not self.pages:
+            raise ValueError("%s holds no image" % filename)
+        first = self.pages[0]
+        n_ij = first.pop("imagej_images", 0)
+        if len(self.pages) == 1 and n_ij > 1:  # ImageJ stack: frames follow each other after the first strip
+            if len(first["offsets"]) != 1 and not first["contiguous"]:
+                raise ValueError("ImageJ stack with non-contiguous first frame")
+            nbytes = first["h"] * first["w"] * first["dtype"].itemsize
+            base = first["offsets"][0]
+            self.pages = [dict(first, offsets=[base + i * nbytes], counts=[nbytes], contiguous=True) for i in range(n_ij)]
+        self.shape = (len(self.pages), first["h"], first["w"])
+        self.dtype = first["dtype"]
+
+    def _read_ifd(self, f, offset, struct):
+        bo = self.bo
+        f.seek(offset)
+        if self.big:
+            n = struct.unpack(bo + "Q", f.read(8))[0]
+            raw = f.read(20 * n + 8)
+            esz, cfmt, vsz = 20, "Q", 8
+        else:
+            n = struct.unpack(bo + "H", f.read(2))[0]
+            raw = f.read(12 * n + 4)
+            esz, cfmt, vsz = 12, "I", 4
+        tags = {}
+        for i in range(n):
+            e = raw[esz * i : esz * (i + 1)]
+            tag, typ = struct.unpack(bo + "HH", e[:4])
+            count = struct.unpack(bo + cfmt, e[4 : 4 + vsz])[0]
+            fmt = self._TYPES.get(typ)
+            if fmt is None:
+                continue
+            size = struct.calcsize(bo + fmt) * count
+            if size <= vsz:
+                data = e[4 + vsz : 4 + vsz + size]
+            else:
+                pos = struct.unpack(bo + cfmt, e[4 + vsz : 4 + 2 * vsz])[0]
+                here = f.tell()
+                f.seek(pos)
+                data = f.read(size)
+                f.seek(here)
+            tags[tag] = data if typ == 2 else struct.unpack(bo + fmt * count, data)
+        nxt = struct.unpack(bo + cfmt, raw[esz * n : esz * n + vsz])[0]
+        return tags, nxt
+
+    def _page(self, tags):
+        one = lambda t, default=None: tags[t][0] if t in tags else default  # noqa: E731
+        w, h = one(256), one(257)
+        if w is None or h is None:
+            raise ValueError("TIFF directory without ImageWidth / ImageLength")
+        if one(259, 1) != 1:
+            raise ValueError("compressed TIFF (Compression tag %d) needs the `tifffile` package" % one(259))
+        if one(277, 1) != 1:
+            raise ValueError("only greyscale TIFF is supported (SamplesPerPixel %d)" % one(277))
+        if 322 in tags or 324 in tags:
+            raise ValueError("tiled TIFF needs the `tifffile` package")
+        bits, fmt = one(258, 1), one(339, 1)
+        kind = {1: "u", 2: "i", 3: "f"}.get(fmt)
+        if kind is None or bits not in (8, 16, 32, 64) or (kind == "f" and bits < 32):
+            raise ValueError("unsupported TIFF sample type (BitsPerSample %d, SampleFormat %d)" % (bits, fmt))
+        dtype = np.dtype("%s%s%d" % (self.bo, kind, bits // 8))
+        offsets, counts = list(tags.get(273, ())), list(tags.get(279, ()))
+        if not offsets:
+            raise ValueError("TIFF directory without StripOffsets")
+        rps = one(278, h)
+        if not counts:
+            counts = [min(rps, h - i * rps) * w * dtype.itemsize for i in range(len(offsets))]
+        contiguous = all(offsets[i] + counts[i] == offsets[i + 1] for i in range(len(offsets) - 1))
+        page = dict(w=int(w), h=int(h), dtype=dtype, offsets=offsets, counts=counts, contiguous=contiguous)
+        desc = tags.get(270)
+        if isinstance(desc, bytes) and desc.startswith(b"ImageJ"):
+            for line in desc.split(b"\n"):
+                if line.startswith(b"images="):
+                    page["imagej_images"] = int(line[7:].strip(b"\x00 "))
+        return page
+
+    def read(self, indices):
+        out = np.empty((len(indices), self.shape[1], self.shape[2]), dtype=self.dtype.newbyteorder("="))
+        with open(self.filename, "rb") as f:
+            for k, i in enumerate(indices):
+                pg = self.pages[i]
+                if (pg["h"], pg["w"]) != self.shape[1:] or pg["dtype"] != self.dtype:
+                    raise ValueError("TIFF page %d differs in shape or type from page 0" % i)
+                flat = out[k].reshape(-1)
+                pos = 0
+                for off, cnt in zip(pg["offsets"], pg["counts"]):
+                    f.seek(off)
+                    part = np.frombuffer(f.read(cnt), dtype=self.dtype)
+                    flat[pos : pos + part.size] = part
+                    pos += part.size
+                if pos != flat.size:
+                    raise ValueError("TIFF page %d is truncated" % i)
+        return out
+
+
+class TiffArray(lazy_data_loader):
+    """Multi-page TIFF movie (dataset.py:131-181): frames are decoded on demand and returned as float32, like the
+    reference.  Decoding goes through `tifffile` when it is installed, otherwise through the built-in reader of
+    uncompressed greyscale TIFF / BigTIFF / ImageJ stacks above."""
+
+    def __init__(self, filename):
+        self.filename = filename
+        try:
+            import tifffile
+        except ImportError:
+            tifffile = None
         self._tf = tifffile
-        with tifffile.TiffFile(filename) as tf:
-            n = len(tf.pages)
-            page = tf.pages[0]
-            self._shape = (n, page.shape[0], page.shape[1])
-            self._dtype = str(page.dtype)
+        if tifffile is not None:
+            with tifffile.TiffFile(filename) as tf:
+                n = len(tf.pages)
+                page = tf.pages[0]
+                self._shape = (n, int(page.shape[0]), int(page.shape[1]))
+            self._plain = None
+        else:
+            self._plain = _PlainTiff(filename)
+            self._shape = self._plain.shape
 
     @property
     def dtype(self):
-        return self._dtype
+        return np.float32
 
     @property
     def shape(self):
         return self._shape
 
     def _compute_at_indices(self, indices):
-        if isinstance(indices, int):
-            indices = [indices]
-        if isinstance(indices, slice):
-            indices = list(range(*indices.indices(self._shape[0])))
-        return self._tf.imread(self.filename, key=indices).squeeze()
+        if isinstance(indices, (int, np.integer)):
+            indices = [int(indices)]
+        elif isinstance(indices, slice):
+            indices = list(range(indices.start or 0, indices.stop or self._shape[0], indices.step or 1))
+        else:
+            indices = [int(i) for i in indices]
+        if self._tf is not None:
+            data = self._tf.imread(self.filename, key=indices)
+        else:
+            data = self._plain.read(indices)
+        return np.asarray(data).squeeze().astype(self.dtype)
 
 
 def _index_rows(t, idx):

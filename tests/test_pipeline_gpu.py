@@ -374,3 +374,25 @@ def test_residual_windows_match_oracle():
     fsel = [0, 450, 1199]
     got, want = arr[fsel, :, :], ref64.to_pmdarray()[fsel, :, :]
     assert np.linalg.norm(got - want) / np.linalg.norm(want) < 1e-4
+
+
+def test_tiff_movie_equals_array(tmp_path):
+    """A multi-page TIFF movie through TiffArray (frames decoded on demand, float32 like the reference's loader) gives
+    the decomposition of the same data passed as an array."""
+    import localmd_b200
+    from test_tiff_reader import write_tiff
+
+    movie = make_movie(600, 30, 28, n_cells=4, seed=5, dtype=np.uint16)
+    path = str(tmp_path / "movie.tif")
+    write_tiff(path, movie, bo="<", rows_per_strip=8)
+    rng = np.random.default_rng(0)
+    nbk = len(O.tile_starts(30, 12)) * len(O.tile_starts(28, 12))
+    d = O.Draws(bg_frames=rng.choice(600, 600, replace=False).tolist(), bg_sketch=rng.standard_normal((600, 12)).astype(np.float32),
+                init_frames=list(range(100, 400)), thresholds=(1.35, 2.3),
+                block_sketches=[[rng.standard_normal((30, 16)).astype(np.float32)] for _ in range(nbk)])
+    kw = dict(max_components=6, background_rank=2, draws=d)
+    a = localmd_b200.localmd_decomposition(movie.astype(np.float32), [12, 12], 300, **kw)
+    b = localmd_b200.localmd_decomposition(localmd_b200.TiffArray(path), [12, 12], 300, **kw)
+    np.testing.assert_array_equal(a.u.indices, b.u.indices)
+    np.testing.assert_allclose(a.s, b.s, rtol=1e-6)
+    np.testing.assert_allclose(a[7, :, :], b[7, :, :], rtol=1e-5, atol=1e-3)

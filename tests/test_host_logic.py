@@ -281,3 +281,58 @@ def test_strip_tables_tc():
         np.testing.assert_allclose(z, ref[:n_local], atol=1e-9)
         if n_bg:
             np.testing.assert_allclose(zbg.sum(0)[:n_bg], ref[n_local:], atol=1e-9)
+
+
+def test_append_components_and_csr_relabelling_cpu():
+    """Device-agnostic host-side tensor logic, run on CPU tensors: the ragged per-block append used by the windowed block
+    fits, and SparseU.csr(row_ids): the relabelled CSR is a permutation of the row segments of the physical CSR and must
+    equal scipy's canonical CSR of the same matrix with rows numbered in Fortran order."""
+    import scipy.sparse as sp
+    import torch
+
+    from localmd_b200.decomposition import SparseU, _append_components
+
+    final = torch.zeros((3, 4, 8))
+    counter = torch.tensor([0, 2, 5])
+    comps = torch.arange(3 * 4 * 8, dtype=torch.float32).reshape(3, 4, 8) + 1
+    n_new = torch.tensor([3, 0, 2])
+    _append_components(final, counter, comps, n_new)
+    assert torch.equal(final[0, :, :3], comps[0, :, :3]) and torch.all(final[0, :, 3:] == 0)
+    assert torch.all(final[1] == 0)
+    assert torch.equal(final[2, :, 5:7], comps[2, :, :2]) and torch.all(final[2, :, :5] == 0) and torch.all(final[2, :, 7:] == 0)
+
+    rng = np.random.default_rng(8)
+    d1, d2, bh, bw, K = 14, 12, 8, 6, 2
+    rows, cols = O.tile_starts(d1, bh), O.tile_starts(d2, bw)
+    starts = np.array([(a, c) for a in rows for c in cols], dtype=np.int32)
+    ranks = rng.integers(1, 4, len(starts)).astype(np.int64)
+    n_local = int(ranks.sum())
+    uv = rng.standard_normal((n_local, bh * bw))
+    uv[rng.uniform(size=uv.shape) < 0.1] = 0.0  # exact zeros are dropped like scipy does
+    bg = rng.standard_normal((K, d1 * d2)).astype(np.float32)
+    su = SparseU(starts, torch.from_numpy(starts), bh, bw, d1, d2, ranks, torch.from_numpy(ranks.astype(np.int32)),
+                 torch.from_numpy(uv), torch.from_numpy(uv.astype(np.float32)), torch.from_numpy(bg))
+    dense = np.zeros((d1 * d2, n_local + K))
+    col = 0
+    qi, qj = np.divmod(np.arange(bh * bw), bw)
+    for b, (i0, j0) in enumerate(starts):
+        pix = (i0 + qi) * d2 + j0 + qj
+        for c in range(ranks[b]):
+            dense[pix, col] = uv[col]
+            col += 1
+    dense[:, n_local:] = bg.T.astype(np.float64)
+    for order in ("C", "F"):
+        row_ids = np.arange(d1 * d2).reshape((d1, d2), order=order).reshape(-1)  # physical pixel -> row id
+        ref = np.zeros_like(dense)
+        ref[row_ids] = dense
+        ref = sp.csr_matrix(ref)
+        ref.sort_indices()
+        ip, ix, v = su.csr(torch.from_numpy(row_ids))
+        np.testing.assert_array_equal(ip.numpy(), ref.indptr)
+        np.testing.assert_array_equal(ix.numpy(), ref.indices)
+        np.testing.assert_array_equal(v.numpy(), ref.data)
+    ip, ix, v = su.csr()
+    refp = sp.csr_matrix(dense)
+    refp.sort_indices()
+    np.testing.assert_array_equal(ip.numpy(), refp.indptr)
+    np.testing.assert_array_equal(ix.numpy(), refp.indices)

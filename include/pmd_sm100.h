@@ -56,7 +56,8 @@ int pmd_standardize_frames(const void* movie, int dtype, int64_t d, const int64_
 /* batched Gram matrices in float64:  C[b] = A[b] A[b]^T  (or A^T A), fp32 inputs, fp64 accumulate.
  * A[b] element (i, m) at a + b*batch_stride + i*row_stride + m*inner_stride, i < n (n <= 112),
  * m < m_len.  C is [batch][n][n] double and must be zeroed by the caller (partial sums are added
- * atomically).  Building block of every small orthogonalisation / SVD below.
+ * atomically).  Rows that are contiguous in memory (inner_stride 1, row_stride a multiple of 4) run on the FP64
+ * tensor cores (mma.sync m8n8k4); other layouts on FMA.  Building block of every small orthogonalisation / SVD below.
  * replaces: the normal-equation half of jnp.linalg.qr / jnp.linalg.svd calls at
  *           decomposition.py:64,66,301,315,319 and pmd_loader.py:58,60. */
 int pmd_gram_f64(const float* a, int64_t batch, int64_t n, int64_t m_len, int64_t batch_stride,

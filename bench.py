@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="N > 1: ONE movie of the workload's size split over the GPUs (default: weak)")
     ap.add_argument("--stage-times", action="store_true", help="print per-stage GPU ms to stderr")
     return ap.parse_args()
 
@@ -95,89 +96,165 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def oracle_draws(T, d1, d2, block, t, r, K, rank_prune_factor, seed=0):
-    """Host-supplied random draws for the CPU baseline (thresholds are simulated by the oracle itself on a
-    reduced number of iterations to keep the baseline bounded)."""
-    import oracle.pmd_oracle as O
-
-    rng = np.random.default_rng(seed)
-    nb = len(O.tile_starts(d1, block)) * len(O.tile_starts(d2, block))
-    n_bg = min(1000, T)
-    sims = 25
-    return O.Draws(
-        bg_frames=rng.choice(T, n_bg, replace=False).tolist(),
-        bg_sketch=rng.standard_normal((n_bg, K + 10), dtype=np.float32),
-        init_frames=list(range(0, t)),
-        sim_noise=[rng.standard_normal((block, block, t), dtype=np.float32) for _ in range(sims)],
-        sim_sketch=[rng.standard_normal((t, 11), dtype=np.float32) for _ in range(sims)],
-        block_sketches=[[rng.standard_normal((t // 10, r + 10), dtype=np.float32)] for _ in range(nb)],
-        prune_sketch=lambda shape: rng.standard_normal(shape, dtype=np.float32),
-    )
+# The bounded sample of the workload that the CPU legs run (the oracle needs ~9 min for one full C2 pass on 16 cores):
+# same block size, same max_components / background rank / rank pruning, same init-window fraction t / T = 1/4 as C2,
+# on a 128x128 crop x 4096 frames.  Throughput is reported in FULL-FIELD-OF-VIEW frame equivalents:
+# sample pixel-frames / (d1 d2 of the workload) / seconds -- measured, not extrapolated per stage.
+SAMPLE = dict(T=4096, d1=128, d2=128, t=1024, n_cells=25, sims=250)
 
 
-def cpu_reference_sample(w, steps=1):
-    """The reference's algorithm (NumPy/SciPy float32 restatement, oracle/pmd_oracle.py) on a bounded
-    sample of the workload: same FOV geometry class and block size, FOV 128x128, T=2048, 1024 init
-    frames.  Returns (frames/s of the sample scaled to the full workload, description, cores)."""
+def sample_inputs(w, seed=0):
+    """(movie, draws, kwargs) of the bounded sample: every random quantity is host supplied so that the oracle and the
+    CUDA path see the same inputs (BASELINE.json north_star: 'same host-supplied random sketch matrices')."""
     import oracle.pmd_oracle as O
 
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from synth import make_movie
 
-    cores = os.cpu_count() or 1
-    T, d1, d2, t = 2048, 128, 128, 1024
-    movie = make_movie(T, d1, d2, n_cells=25, seed=5, blob_sigma=w["blob"])
-    draws = oracle_draws(T, d1, d2, w["block"], t, 50, 15, 0.33)
-    best = None
-    stages = {}
-    for _ in range(steps):
-        tm = {}
-        t0 = time.perf_counter()
-        O.localmd_decomposition_oracle(movie, [w["block"], w["block"]], t, draws, rank_prune=True, timings=tm)
-        dt = time.perf_counter() - t0
-        if best is None or dt < best:
-            best, stages = dt, tm
-    # scale: full-movie passes ~ pixels*T; block stage ~ blocks * t; thresholds fixed count; whitening/final ~ k^2 T
-    full_pix_T = w["d1"] * w["d2"] * w["T"]
-    s_pass = full_pix_T / (d1 * d2 * T)
-    s_blk = (w["d1"] * w["d2"] * w["frames_to_init"]) / (d1 * d2 * t)
-    est = (stages.get("stats", 0) + stages.get("projection", 0)) * s_pass + (
-        stages.get("blocks", 0) + stages.get("init_filter", 0) + stages.get("background", 0)) * s_blk + (
-        stages.get("thresholds", 0) * 10 * (w["frames_to_init"] / t)) + (stages.get("whiten", 0) + stages.get("final_svd", 0)) * s_pass
-    sample = ("restated reference (NumPy/SciPy float32, not JAX): %dx%dx%d movie, %dx%d blocks, %d init frames, rank_prune, "
-              "%.1f s measured; stage times scaled to the full workload (passes ~ pixels*T, block stage ~ blocks*t)"
-              % (d1, d2, T, w["block"], w["block"], t, best))
-    return w["T"] / est, T / best, sample, cores, stages
+    T, d1, d2, t, blk, r, K = SAMPLE["T"], SAMPLE["d1"], SAMPLE["d2"], SAMPLE["t"], w["block"], 50, 15
+    movie = make_movie(T, d1, d2, n_cells=SAMPLE["n_cells"], seed=5, blob_sigma=w["blob"])
+    rng = np.random.default_rng(seed)
+    nb = len(O.tile_starts(d1, blk)) * len(O.tile_starts(d2, blk))
+    n_bg = min(1000, T)
+    sims = SAMPLE["sims"]
+    prune_seed = int(rng.integers(0, 2**31))
+    draws = O.Draws(
+        bg_frames=rng.choice(T, n_bg, replace=False).tolist(),
+        bg_sketch=rng.standard_normal((n_bg, K + 10), dtype=np.float32),
+        init_frames=list(range(t, 2 * t)),
+        sim_noise=[rng.standard_normal((blk, blk, t), dtype=np.float32) for _ in range(sims)],
+        sim_sketch=[rng.standard_normal((t, 11), dtype=np.float32) for _ in range(sims)],
+        block_sketches=[[rng.standard_normal((t // 10, r + 10), dtype=np.float32)] for _ in range(nb)],
+        prune_sketch=lambda shape: np.random.default_rng(prune_seed).standard_normal(shape, dtype=np.float32),
+    )
+    kw = dict(block_sizes=[blk, blk], frame_range=t, rank_prune=True, max_components=r, background_rank=K)
+    return movie, draws, kw
+
+
+def sample_description(w, seconds):
+    return ("restated reference (NumPy/SciPy float32 oracle, not JAX) on a bounded sample of the workload: %dx%d crop x %d frames, "
+            "%dx%d blocks, %d init frames, max_components 50, background rank 15, rank_prune 0.33, %d threshold simulations; "
+            "%.1f s measured; value = sample pixel-frames / (%d x %d) / seconds (full-FOV frame equivalents, measured, not "
+            "extrapolated)" % (SAMPLE["d1"], SAMPLE["d2"], SAMPLE["T"], w["block"], w["block"], SAMPLE["t"], SAMPLE["sims"],
+                               seconds, w["d1"], w["d2"]))
+
+
+def cpu_reference_pass(w, inputs=None, keep_result=False):
+    """One pass of the reference's algorithm (oracle/pmd_oracle.py) over the bounded sample on all host cores.
+    Returns dict(seconds, value, stages, result)."""
+    import oracle.pmd_oracle as O
+
+    movie, draws, kw = inputs if inputs is not None else sample_inputs(w)
+    tm = {}
+    t0 = time.perf_counter()
+    res = O.localmd_decomposition_oracle(movie, kw["block_sizes"], kw["frame_range"], draws, rank_prune=True,
+                                         max_components=kw["max_components"], background_rank=kw["background_rank"], timings=tm)
+    dt = time.perf_counter() - t0
+    equiv_frames = SAMPLE["T"] * (SAMPLE["d1"] * SAMPLE["d2"]) / float(w["d1"] * w["d2"])
+    return dict(seconds=dt, value=equiv_frames / dt, stages=tm, result=res if keep_result else None)
 
 
 # ------------------------------------------------------------------------------------------------
 def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port; JAX is not installable here) on the box's host
+    cores.  Every step is one full pass over the bounded sample; warm-up and step counts are honoured as given."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = WORKLOADS[args.workload]
-    vals = []
+    cores = os.cpu_count() or 1
+    inputs = sample_inputs(w)
+    secs = []
     for i in range(args.warmup + args.steps):
-        scaled, raw, sample, cores, stages = cpu_reference_sample(w)
+        p = cpu_reference_pass(w, inputs)
         if i >= args.warmup:
-            vals.append(scaled)
-        if i == 0 and args.warmup + args.steps > 2:
-            # one pass already costs ~10-30 s of CPU: bound the run
-            args.warmup, args.steps = min(args.warmup, 1), min(args.steps, 1)
-    v = float(np.mean(vals)) if vals else scaled
+            secs.append(p["seconds"])
+    sec = float(np.mean(secs))
+    equiv_frames = SAMPLE["T"] * (SAMPLE["d1"] * SAMPLE["d2"]) / float(w["d1"] * w["d2"])
+    v = equiv_frames / sec
+    cfg = workload_config(args.workload, args.gpus)
+    cfg["workload"] = "bounded sample of: " + cfg["workload"]
+    cfg["sample"] = dict(SAMPLE, block=w["block"], frames_equivalent_per_step=equiv_frames)
+    cfg["timing"] = "host wall clock (perf_counter) around every oracle pass, all host cores"
+    cfg["parallelism"] = "rank 0 only, %d host threads" % cores
     line = {
         "impl": "reference", "metric": "frames/sec compressed", "value": v, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * w["T"] / v, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, args.gpus),
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "extrapolated": False,
+        "config": cfg,
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample_description(w, sec)},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(name, n_gpus):
+def parity_on_sample(w, dev, inputs, ref):
+    """The CUDA path on the bounded sample with the SAME host-supplied draws as the oracle pass `ref`; the oracle is also
+    evaluated in float64 (the reference algorithm in exact-ish arithmetic) to separate float32 rounding of the CPU
+    restatement from differences of the CUDA path.  Returns the `parity` object of the JSON line."""
+    import localmd_b200
+    import oracle.pmd_oracle as O
+    from oracle import parity as P
+
+    movie, draws, kw = inputs
+    det = {}
+    arr = localmd_b200.localmd_decomposition(movie, draws=draws, details=det, device=dev, **kw)
+    rep32 = P.parity_report(arr, det, ref)
+    with O.precision(np.float64):
+        ref64 = O.localmd_decomposition_oracle(movie, kw["block_sizes"], kw["frame_range"], draws, rank_prune=True,
+                                               max_components=kw["max_components"], background_rank=kw["background_rank"])
+    rep64 = P.parity_report(arr, det, ref64)
+    fake = type("A", (), dict(u=ref.u, r=ref.r, s=ref.s, v=ref.vt))()
+    det_o = dict(ranks=ref.ranks, sstat=det["sstat"], tstat=det["tstat"], thresholds=ref.thresholds)
+    floor = P.parity_report(fake, det_o, ref64) if np.array_equal(ref.ranks, ref64.ranks) else None
+    return {
+        "sample": "%dx%dx%d crop, %dx%d blocks, t=%d, max_components %d, rank_prune 0.33, same host-supplied draws"
+                  % (SAMPLE["d1"], SAMPLE["d2"], SAMPLE["T"], w["block"], w["block"], SAMPLE["t"], kw["max_components"]),
+        "tolerances": {"ranks/CSR": "bit-exact outside eps_stat of a threshold", "s_rel": 1e-4, "angle_rad": 1e-3, "yhat_rel_fro": 1e-4},
+        "vs_oracle_f64": rep64, "within_north_star_f64": P.within_north_star(rep64),
+        "vs_oracle_f32": rep32,
+        "oracle_f32_vs_f64": None if floor is None else {k: floor[k] for k in ("s_max_rel_err_lead", "angle_UR_max_rad", "angle_Vt_max_rad",
+                                                                               "yhat_rel_fro_err")},
+        "mean_rank": float(np.mean(det["ranks"])), "max_rank": int(np.max(det["ranks"])),
+    }
+
+
+def multi_gpu_parity(dev, group, rank, world):
+    """N > 1: the frame-sharded decomposition of one small movie equals its single-GPU decomposition (same draws)."""
+    import localmd_b200
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from synth import make_movie
+
+    T, d1, d2 = 1024 * max(world, 4), 64, 72
+    movie = make_movie(T, d1, d2, n_cells=8, seed=11)
+    kw = dict(block_sizes=[16, 16], frame_range=1500, max_components=10, background_rank=3, seed=5, rank_prune=True)
+    det = {}
+    arr = localmd_b200.localmd_decomposition(movie, device=dev, group=group, details=det, **kw)
+    out = None
+    if rank == 0:
+        det1 = {}
+        one = localmd_b200.localmd_decomposition(movie, device=dev, details=det1, **kw)
+        lead = one.s > 0.05 * one.s[0]
+        frames = [0, 1023, 1024, T // 2, T - 1]
+        rec, rec1 = arr[frames], one[frames]
+        out = {"movie": "%dx%dx%d, 16x16 blocks, sharded x%d vs single GPU" % (d1, d2, T, world),
+               "ranks_equal": bool(np.array_equal(det["ranks"], det1["ranks"])), "k": [int(len(arr.s)), int(len(one.s))],
+               "s_max_rel_err_lead": float(np.max(np.abs(arr.s[: len(one.s)][lead] / one.s[lead] - 1))) if len(arr.s) >= len(one.s) else None,
+               "recon_rel_err": float(np.linalg.norm(rec - rec1) / np.linalg.norm(rec1 - one.mean_img[None])),
+               "mean_max_rel_err": float(np.max(np.abs(arr.mean_img / one.mean_img - 1)))}
+        out["ok"] = bool(out["ranks_equal"] and out["s_max_rel_err_lead"] is not None and out["s_max_rel_err_lead"] <= 1e-4
+                         and out["recon_rel_err"] <= 1e-4)
+    import torch.distributed as dist
+
+    dist.barrier()
+    return out
+
+
+def workload_config(name, n_gpus, strong=False):
     w = WORKLOADS[name]
+    if strong and n_gpus > 1:
+        w = dict(w, T=w["T"] // n_gpus)
     which = {"c2": "BASELINE.json configs[1]", "c3": "BASELINE.json configs[2]", "c4": "BASELINE.json configs[3], per-GPU shard"}
     gb = 4.0 * w["d1"] * w["d2"] * w["T"] / 1e9
     return {"workload": "synthetic %dx%dx%d float32 %s movie, block %dx%d, frames_to_init %d, rank_prune 0.33 (%s)"
@@ -219,7 +296,7 @@ def run_ours(args):
     # weak scaling: ONE movie of world * T frames, frame-sharded over the ranks (1024-aligned contiguous ranges);
     # the stats and projection passes run on the local shard, the block stage is partitioned by blocks, the rank-sized
     # reductions / gathers go over NCCL (DESIGN.md section "multi-GPU")
-    t_total = world * T
+    t_total = T if args.strong else world * T
     lo, hi = sharding.shard_bounds(t_total, world)[rank]
     shard = make_movie(t_total, d1, d2, n_cells=w["n_cells"], blob_sigma=w["blob"], bg_rank=w["bg_rank"], seed=1234, device=dev,
                        frame_lo=lo, frame_hi=hi)
@@ -355,22 +432,33 @@ def run_ours(args):
                    "h2d_bytes_per_step": int(det.get("__info__", {}).get("h2d_bytes", host_t.numel() * host_t.element_size())) * world,
                    "d2h_bytes_per_step": d2h, "ms": e2e_ms, "passes": len(e2e_runs)}
 
+    mgpu = multi_gpu_parity(dev, group, rank, world) if world > 1 else None
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
         return
     line = {
         "metric": "frames/sec compressed", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, world), "clocks": clocks,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.strong and world > 1 else "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args.workload, world, args.strong), "clocks": clocks,
         "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "pmdarray_reconstruction": pmdarray,
         "stage_ms": {k: round(float(np.mean([p[k] for p in per_step])), 3) for k in per_step[0]
                      if isinstance(per_step[0][k], float) and "." not in k},
     }
+    if mgpu is not None:
+        line["multi_gpu_parity"] = mgpu
     if not args.no_cpu_baseline and world == 1:
-        scaled, raw, sample, cores, _ = cpu_reference_sample(w)
-        line["cpu_baseline"] = {"value": scaled, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
-                                "sample_frames_per_s": raw}
+        # CPU leg (rank 0, N = 1 only): ONE measured oracle pass over the bounded sample, then the CUDA path on the same
+        # sample and draws -> parity block
+        inputs = sample_inputs(w)
+        p = cpu_reference_pass(w, inputs, keep_result=True)
+        line["cpu_baseline"] = {"value": p["value"], "unit": "frames/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": sample_description(w, p["seconds"]), "seconds": p["seconds"],
+                                "stage_s": {k: round(v, 3) for k, v in p["stages"].items()}}
+        try:
+            line["parity"] = parity_on_sample(w, dev, inputs, p["result"])
+        except Exception as exc:  # the bench line must still be printed; a failed parity run is reported as such
+            line["parity"] = {"error": repr(exc)}
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())
 

@@ -265,6 +265,47 @@ int pmd_pack_strips_tc(const int32_t* items, const int32_t* item_of_row, int64_t
                        const int32_t* tasks, const float* uvals, int64_t bpix, const float* bg, int64_t d, int64_t d2,
                        void* bimg, void* stream);
 
+/* K7, movie operand in TENSOR MEMORY (tcgen05 TS form, TMA-fed; sm_100a): the projection of pmd_project_stream_tc with
+ *   - column strips that partition every image row exactly (no halo: every movie element is read from HBM once),
+ *   - raw movie tiles [128 frames x 32 pixels] fetched by 2-D TMA boxes (cp.async.bulk.tensor) in strip-fastest grid
+ *     order, centred and split by converter warps and written straight into tensor memory (A operand of the MMAs),
+ *   - N = 96 / 128 / 192 slot columns with 384 / N frame tiles of 128 frames per CTA (chosen by pmd_make_strips_ts),
+ *   - 1 / std folded into the coefficient images (pmd_pack_strips_ts); mean may be NULL.
+ * Tables come from pmd_make_strips_ts:
+ *   items:  [n_items][12] int32 = (first column c0, 32-pixel chunks per row, first row, rows, first image chunk,
+ *           first event, events, bg partial index, first slot_ptr entry, 0, 0, 0)
+ *   events: [n][4] int32 = (row, slot, first output column, n comps | kind << 8), ascending per item: after that row the
+ *           slot is read and cleared; kind 0 stores finished local columns to z, kind 1 ADDS a partial sum of background
+ *           columns to zbg (zero on entry), kind 2 atomically ADDS the partial sum of a block shared by two strips to z
+ *           (those rows of z must be zero on entry; two commuting contributions: the result is order independent)
+ *   bimg:   per (item, row, chunk) 2 N 128 bytes: [N columns][32 pixels] TF32 part + bf16 pair part, SWIZZLE_128B
+ * Needs d2 % 4 == 0, a 16-byte aligned movie whose frame pitch AND image-row pitch in bytes are multiples of 16.
+ * replaces: pmd_loader.py:316-346, 392-414 (v_projection / v_projection_routine) in full. */
+int pmd_project_stream_ts(const void* movie, int dtype, int64_t t, int64_t d2, int64_t d, const int32_t* items,
+                          int64_t n_items, const int32_t* events, const void* bimg, int64_t n, const float* mean, float* z,
+                          int64_t ldz, float* zbg, int64_t ldzbg, int64_t bg_stride, void* stream);
+
+/* HOST function (every pointer is a HOST pointer): tables of pmd_project_stream_ts.  w_fixed / n_fixed > 0 force the
+ * strip width (32, 64, 96, 128 pixels) / the slot columns N, otherwise both are chosen by a cost model.  Outputs (caller
+ * allocated): items [cap_items][12], slot_ptr [cap_items*49], tasks [cap_tasks][8] = (first row, first column relative
+ * to c0 (may be negative), rows, width, first output column, n comps, kind 0 whole block | 1 background | 2 block shared
+ * by two strips, 0), events [cap_events][4], counts[8] = (n_items, n_tasks, n_events, image chunks, n_parts, W, N,
+ * frame tiles per CTA); counts[0] == 0: geometry not supported (blocks wider than 129 pixels).
+ * replaces: nothing in the reference (host bookkeeping of the new projection kernel). */
+int pmd_make_strips_ts(const int32_t* row_starts, int64_t nbr, const int32_t* col_starts, int64_t nbc, int64_t bh,
+                       int64_t bw, int64_t d1, int64_t d2, const int64_t* ranks, const int64_t* col0, int64_t n_bg,
+                       int64_t w_fixed, int64_t n_fixed, int32_t* items_out, int64_t cap_items, int32_t* slot_ptr_out,
+                       int32_t* tasks_out, int64_t cap_tasks, int32_t* events_out, int64_t cap_events, int64_t* counts);
+
+/* Coefficient images of pmd_project_stream_ts on the device: one CTA per (item, row) pair listed in item_of_row
+ * [n_rows_total][2] = (item, row - first row of the item).  uvals: block-component values [column][bh*bw] float32,
+ * bg: [K][d] float32 dense background rows (may be NULL when there are none), inv_std: [d] or NULL (folded into the
+ * coefficients), n: slot columns N of the tables.
+ * replaces: nothing in the reference (operand packing of the new projection kernel). */
+int pmd_pack_strips_ts(const int32_t* items, const int32_t* item_of_row, int64_t n_rows_total, const int32_t* slot_ptr,
+                       const int32_t* tasks, const float* uvals, int64_t bpix, const float* bg, const float* inv_std,
+                       int64_t d, int64_t d2, int64_t n, void* bimg, void* stream);
+
 /* K7b  full-movie projection onto dense (background) columns:
  *   z[c][f] += sum_p basis[c][p] * (movie[f][p] - mean[p]) * inv_std[p]     (c < k <= 16)
  * replaces: the same v_projection for the dense background columns appended at

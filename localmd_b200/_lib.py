@@ -7,7 +7,7 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpmd_sm100.so")
+LIB_PATH = os.environ.get("PMD_LIB_PATH") or os.path.join(HERE, "libpmd_sm100.so")   # override: debug builds of the library
 HEADER_PATH = os.path.join(HERE, "..", "include", "pmd_sm100.h")
 
 _lib = None

@@ -489,15 +489,22 @@ class SparseU:
         regular = len(ranks_host) > 0 and len(rows) * len(cols) == len(ranks_host) and np.array_equal(
             st64, np.stack(np.meshgrid(rows, cols, indexing="ij"), axis=-1).reshape(-1, 2))
         self.strips_tc = None
+        self.strips_ts = None
         self._regular = (rows, cols) if regular else None
         self._tc_host = None
-        if regular and os.environ.get("PMD_K7", "tc") != "simt":
+        self._ts_host = None
+        which = os.environ.get("PMD_K7", "ts")   # development switch between the generations of the projection kernel
+        if regular and which == "ts":
+            # K7 with TMA-fed raw tiles and the movie operand in tensor memory (csrc/project_ts.cu): host tables now
+            # (native library), device tables and coefficient images at the first projection call
+            self._ts_host = ops.make_strips_ts(rows, cols, bh, bw, d1, d2, ranks_host, self.col0_host, bg.shape[0])
+        if regular and self._ts_host is None and which != "simt":
             # K7 on the tensor cores (csrc/project_tc.cu): host tables now (native library), device tables and
             # coefficient images at the first projection call
             self._tc_host = ops.make_strips_tc(rows, cols, bh, bw, d1, d2, ranks_host, self.col0_host, bg.shape[0])
-        if regular and self._tc_host is None:
+        if regular and self._tc_host is None and self._ts_host is None:
             self._build_simt_strips()
-        if self.strips is None and self._tc_host is None:
+        if self.strips is None and self._tc_host is None and self._ts_host is None:
             self._build_supertiles()
 
     def _build_supertiles(self):
@@ -519,6 +526,19 @@ class SparseU:
         dev = self.ranks_dev.device
         self.strips_tc = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
         self.bimg = ops.pack_strips_tc(self.strips_tc, self.uvals32, self.bg, self.bh * self.bw, self.d2)
+
+    def _finish_ts(self, inv_std):
+        """Upload the tables of the TMA / tensor-memory kernel and build its coefficient images with 1 / std folded in
+        (once per decomposition, at the first projection call)."""
+        st = self._ts_host
+        if st is not None:
+            self._ts_host = None
+            dev = self.ranks_dev.device
+            self.strips_ts = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+            self._ts_inv = None
+        if self.strips_ts is not None and (getattr(self, "bimg_ts", None) is None or self._ts_inv is not inv_std):
+            self.bimg_ts = ops.pack_strips_ts(self.strips_ts, self.uvals32, self.bg, inv_std, self.bh * self.bw, self.d2)
+            self._ts_inv = inv_std
 
     def _build_simt_strips(self):
         """Tables of the SIMT strip-streaming kernel (fallback of the tensor-core path: unaligned movies, tiny FOVs)."""
@@ -635,6 +655,18 @@ class SparseU:
     def project(self, movie2d, mean, inv_std, z):
         """z[:, :n] (R, ldz) (+)= U^T standardised(movie2d)   (K7a + K7b)."""
         n = movie2d.shape[0]
+        if (self._ts_host is not None or self.strips_ts is not None) and ops.project_stream_ts_ok(movie2d, self.d2, mean):
+            self._finish_ts(inv_std)
+            ops.project_stream_ts(movie2d, self.d2, self.strips_ts, self.bimg_ts, mean, z[: self.n_local], z[self.n_local :])
+            _submark("projection.stream")
+            return
+        if self._ts_host is not None or self.strips_ts is not None:   # unaligned movie: the older strip kernels
+            if self._tc_host is None and self.strips_tc is None and self._regular is not None:
+                rows, cols = self._regular
+                self._tc_host = ops.make_strips_tc(rows, cols, self.bh, self.bw, self.d1, self.d2, self.ranks_host, self.col0_host,
+                                                   self.bg.shape[0])
+                if self._tc_host is None and self.strips is None:
+                    self._build_simt_strips()
         self._finish_tc()
         if self.strips_tc is not None:
             if ops.project_stream_tc_ok(movie2d, self.d2, mean, inv_std):

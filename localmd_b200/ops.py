@@ -860,3 +860,84 @@ def project_stream_tc(movie2d, d2, st_dev, bimg, mean, inv_std, z_local, z_bg):
           max(K, 1) * t, _stream())
     if K:
         z_bg[:, :t].copy_(parts[:, :K].sum(dim=0))
+
+
+# ---- K7, movie operand in tensor memory (csrc/project_ts.cu, strips_ts_host.cu) ------------------------------------
+TS_MAX_SLOTS = 48
+
+
+def make_strips_ts(row_starts, col_starts, bh, bw, d1, d2, ranks_host, col0_host, n_bg, W=None, N=None):
+    """Host tables for pmd_project_stream_ts (native routine pmd_make_strips_ts).  Returns a dict of numpy tables, or
+    None when the geometry is not supported (callers then use the older kernels)."""
+    rs = np.ascontiguousarray(row_starts, dtype=np.int32)
+    cs = np.ascontiguousarray(col_starts, dtype=np.int32)
+    ranks = np.ascontiguousarray(ranks_host, dtype=np.int64).reshape(-1)
+    col0 = np.ascontiguousarray(col0_host, dtype=np.int64).reshape(-1)
+    n_bg = int(n_bg)
+    n_strips_max = (int(d2) + 31) // 32
+    # a block gives a task to at most two strips
+    cap_tasks = 2 * int(((ranks + 3) // 4).sum()) + n_strips_max * ((n_bg + 3) // 4) + 8
+    cap_items = n_strips_max + cap_tasks
+    items = np.zeros((cap_items, 12), np.int32)
+    slot_ptr = np.zeros(cap_items * (TS_MAX_SLOTS + 1), np.int32)
+    tasks = np.zeros((cap_tasks, 8), np.int32)
+    cap_events = cap_tasks + ((n_bg + 3) // 4) * (n_strips_max + 4) * (int(d1) + 2)  # local tasks + background drains
+    events = np.zeros((cap_events, 4), np.int32)
+    counts = np.zeros(8, np.int64)
+    rc = _lib.lib().pmd_make_strips_ts(_np_ptr(rs), len(rs), _np_ptr(cs), len(cs), int(bh), int(bw), int(d1), int(d2),
+                                       _np_ptr(ranks), _np_ptr(col0), n_bg, int(W or 0), int(N or 0), _np_ptr(items), cap_items,
+                                       _np_ptr(slot_ptr), _np_ptr(tasks), cap_tasks, _np_ptr(events), cap_events, _np_ptr(counts))
+    _lib.check(rc, "pmd_make_strips_ts")
+    n_items, n_tasks, n_ev, chunks, n_parts, w, n, tiles = (int(x) for x in counts[:8])
+    if n_items == 0:
+        return None
+    items = items[:n_items].copy()
+    item_of_row = np.concatenate([np.stack([np.full(int(it[3]), i, np.int32), np.arange(int(it[3]), dtype=np.int32)], axis=1)
+                                  for i, it in enumerate(items)], axis=0)
+    tk = tasks[:n_tasks]
+    return dict(items=items, slot_ptr=slot_ptr[: n_items * (TS_MAX_SLOTS + 1)].copy(), tasks=tk.copy(),
+                events=events[:n_ev].copy(), item_of_row=np.ascontiguousarray(item_of_row), chunks=chunks, n_parts=n_parts,
+                W=w, N=n, tiles=tiles, n_items=n_items, has_shared=bool((tk[:, 6] == 2).any()))
+
+
+def pack_strips_ts(st_dev, uvals32, bg, inv_std, bpix, d2):
+    """Coefficient images (uint8 tensor, 2 N 128 bytes per (item, row, 32-pixel chunk)) of pmd_project_stream_ts, with
+    1 / std folded in.  st_dev: make_strips_ts() tables with the arrays as device tensors."""
+    dev = st_dev["items"].device
+    n = st_dev["N"]
+    bimg = torch.empty(st_dev["chunks"] * 2 * n * 128, dtype=torch.uint8, device=dev)
+    uv = uvals32 if uvals32.numel() else torch.zeros((1, bpix), dtype=torch.float32, device=dev)
+    have_bg = bg is not None and bg.numel() > 0
+    d = bg.shape[1] if have_bg else (inv_std.numel() if inv_std is not None else d2)
+    if inv_std is not None:
+        _req(inv_std, torch.float32, "inv_std")
+    _call("pmd_pack_strips_ts", _p(st_dev["items"]), _p(st_dev["item_of_row"]), st_dev["item_of_row"].shape[0],
+          _p(st_dev["slot_ptr"]), _p(st_dev["tasks"]), _p(_req(uv, torch.float32, "uvals")), bpix, _p(bg) if have_bg else None,
+          _p(inv_std), d, d2, n, _p(bimg), _stream())
+    return bimg
+
+
+def project_stream_ts_ok(movie2d, d2, mean):
+    """Alignment requirements of the TMA-fed projection kernel."""
+    pitch = movie2d.shape[1] * movie2d.element_size()
+    # every TMA box starts at a multiple of 32 pixels of an image row: rows and frames must start on 16-byte boundaries
+    ok = (d2 % 4 == 0 and movie2d.data_ptr() % 16 == 0 and movie2d.stride(0) == movie2d.shape[1] and pitch % 16 == 0
+          and (d2 * movie2d.element_size()) % 16 == 0)
+    return ok and (mean is None or mean.data_ptr() % 16 == 0)
+
+
+def project_stream_ts(movie2d, d2, st_dev, bimg, mean, z_local, z_bg):
+    """K7 (TMA + tensor-memory operand): z_local[col, f] and z_bg[k, f] of U^T standardised movie in one streaming pass.
+    `bimg` must have been packed with the inv_std this projection is meant to apply (pack_strips_ts)."""
+    t, d = movie2d.shape
+    assert z_local.dtype == torch.float32 and (z_local.numel() == 0 or z_local.stride(1) == 1)
+    K = z_bg.shape[0]
+    parts = torch.zeros((st_dev["n_parts"], max(K, 1), t), dtype=torch.float32, device=movie2d.device)
+    zl = z_local if z_local.numel() else parts
+    if st_dev["has_shared"] and z_local.numel():
+        z_local[:, :t].zero_()   # blocks shared by two strips are accumulated by two atomic adds
+    _call("pmd_project_stream_ts", _p(movie2d), movie_dtype_code(movie2d), t, d2, d, _p(st_dev["items"]), st_dev["n_items"],
+          _p(st_dev["events"]), _p(bimg), st_dev["N"], _p(mean), _p(zl), zl.stride(0) if z_local.numel() else t, _p(parts), t,
+          max(K, 1) * t, _stream())
+    if K:
+        z_bg[:, :t].copy_(parts[:, :K].sum(dim=0))

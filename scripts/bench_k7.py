@@ -87,6 +87,30 @@ if which in ("all", "tc", "stream"):
     sel = ref.abs().sum(1) > 0
     err = ((z2[:, :n].double() - ref)[sel].abs().max() / ref.abs().max()).item()
     print("tc vs float64 reference (sampled blocks + background): max abs err / max |ref| = %.3e" % err)
+if which in ("all", "ts"):
+    Wf = int(os.environ.get("PMD_TS_W", "0")) or None
+    Nf = int(os.environ.get("PMD_TS_N", "0")) or None
+    sst = ops.make_strips_ts(rows, cols, bh, bw, d1, d2, ranks, col0, K, W=Wf, N=Nf)
+    sst_d = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in sst.items()}
+    bimg_ts = ops.pack_strips_ts(sst_d, uv, bg, inv, bh * bw, d2)
+    it = sst["items"]
+    print("ts strips: W", sst["W"], "N", sst["N"], "tiles", sst["tiles"], "items", sst["n_items"], "image MB", bimg_ts.numel() / 1e6,
+          "streamed/ideal %.3f" % (float((it[:, 1] * it[:, 3]).sum()) * 32 / (d1 * d2)))
+    z3 = torch.zeros_like(z)
+    timeit("pack_strips_ts", lambda: ops.pack_strips_ts(sst_d, uv, bg, inv, bh * bw, d2))
+    timeit("project_stream_ts", lambda: ops.project_stream_ts(movie, d2, sst_d, bimg_ts, mean, z3[:n_local], z3[n_local:]))
+    n = min(T, 512)
+    ref = torch.zeros((n_local + K, n), dtype=torch.float64, device=dev)
+    yc = ((movie[:n, : d1 * d2].double() - mean.double()) * inv.double())
+    ref[n_local:] = bg.double() @ yc.t()
+    qi, qj = np.divmod(np.arange(bh * bw), bw)
+    for b in range(0, nb, max(1, nb // 64)):
+        i0, j0 = rows[b // len(cols)], cols[b % len(cols)]
+        pix = torch.from_numpy((i0 + qi) * d2 + j0 + qj).to(dev)
+        ref[col0[b] : col0[b] + ranks[b]] = uv[col0[b] : col0[b] + ranks[b]].double() @ yc[:, pix].t()
+    sel = ref.abs().sum(1) > 0
+    err = ((z3[:, :n].double() - ref)[sel].abs().max() / ref.abs().max()).item()
+    print("ts vs float64 reference (sampled blocks + background): max abs err / max |ref| = %.3e" % err)
 if which in ("all", "supertile"):
     timeit("project_supertile", lambda: ops.project_supertile(movie, d2, std, bh, bw, uv, mean, inv, z[:n_local]))
 if which in ("all", "local"):

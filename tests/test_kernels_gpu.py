@@ -534,6 +534,56 @@ def test_project_stream_tc(ops, bh, bw, max_rank, dtype, d1, d2, K, T, G):
         np.testing.assert_allclose(z2.cpu().numpy(), ref2[: n_local + K], rtol=0, atol=2e-5 * np.abs(ref2).max())
 
 
+@pytest.mark.parametrize(
+    "bh,bw,max_rank,dtype,d1,d2,K,T,W,N",
+    [(20, 20, 9, np.float32, 60, 128, 15, 700, None, None), (20, 20, 9, np.uint16, 50, 104, 15, 300, 32, 96), (20, 20, 9, np.uint16, 50, 100, 15, 300, 32, 96),
+     (16, 16, 12, np.float32, 70, 96, 5, 1100, 64, 128), (22, 22, 20, np.int16, 61, 88, 9, 258, None, None),
+     (20, 12, 6, np.float32, 64, 40, 16, 513, None, 192), (20, 20, 2, np.float64, 24, 32, 2, 64, None, None),
+     (32, 32, 6, np.uint8, 70, 96, 3, 260, 64, None), (40, 40, 11, np.float32, 90, 104, 4, 255, None, None),
+     (20, 20, 50, np.float32, 60, 80, 0, 130, None, None), (20, 20, 4, np.int32, 50, 60, 2, 129, 128, 96),
+     (40, 40, 30, np.float32, 128, 256, 15, 400, None, None), (20, 20, 6, np.float32, 128, 500, 15, 385, None, None)],
+)
+def test_project_stream_ts(ops, bh, bw, max_rank, dtype, d1, d2, K, T, W, N):
+    """K7 with TMA-fed raw tiles and the movie operand in tensor memory (tcgen05 TS form), exact-partition strips with
+    atomically added partial sums of blocks shared by two strips, 1/std folded into the coefficient images: local + dense
+    columns in one pass, against float64 U^T Y.  Tolerance as for the other K7 kernels (float32-accurate)."""
+    rng = np.random.default_rng(bh * 5 + max_rank)
+    starts, ranks, col0, uv, bg, U = _random_sparse_u(rng, d1, d2, bh, bw, max_rank, K)
+    y = rng.uniform(0, 200, size=(T, d1 * d2))
+    movie = (np.rint(y) if np.issubdtype(dtype, np.integer) else y).astype(dtype)
+    mean = rng.uniform(80, 120, d1 * d2).astype(np.float32)
+    std = rng.uniform(0.5, 2, d1 * d2).astype(np.float32)
+    inv = (1.0 / std).astype(np.float32)
+    n_local = int(ranks.sum())
+    st = ops.make_strips_ts(O.tile_starts(d1, bh), O.tile_starts(d2, bw), bh, bw, d1, d2, ranks, col0, K, W=W, N=N)
+    assert st is not None
+    if W:
+        assert st["W"] == W
+    if N:
+        assert st["N"] == N
+    std_ = {k: (dev(v) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+    bgd = dev(bg) if K else None
+    bimg = ops.pack_strips_ts(std_, dev(uv), bgd, dev(inv), bh * bw, d2)
+    z = torch.full((n_local + K, T + 5), 7.0, dtype=torch.float32, device="cuda")
+    mv = dev(movie)
+    if not ops.project_stream_ts_ok(mv, d2, dev(mean)):
+        with pytest.raises(Exception):   # rejected by the entry point as well (callers fall back to the older kernels)
+            ops.project_stream_ts(mv, d2, std_, bimg, dev(mean), z[:n_local], z[n_local:])
+        return
+    ops.project_stream_ts(mv, d2, std_, bimg, dev(mean), z[:n_local], z[n_local:])
+    yc = (movie.astype(np.float32).astype(np.float64) - mean) / std
+    ref = U.T @ yc.T
+    got = z.cpu().numpy()
+    np.testing.assert_allclose(got[:, :T], ref[: n_local + K], rtol=0, atol=2e-5 * np.abs(ref).max())
+    assert np.all(got[:, T:] == 7.0)  # nothing written beyond the movie
+    if dtype == np.float32:
+        bimg2 = ops.pack_strips_ts(std_, dev(uv), bgd, None, bh * bw, d2)
+        z2 = torch.zeros((n_local + K, T), dtype=torch.float32, device="cuda")
+        ops.project_stream_ts(mv, d2, std_, bimg2, None, z2[:n_local], z2[n_local:])
+        ref2 = U.T @ movie.astype(np.float64).T
+        np.testing.assert_allclose(z2.cpu().numpy(), ref2[: n_local + K], rtol=0, atol=2e-5 * np.abs(ref2).max())
+
+
 def test_project_without_standardisation(ops):
     rng = np.random.default_rng(9)
     d1, d2, T, K, bh, bw = 40, 36, 50, 2, 16, 16

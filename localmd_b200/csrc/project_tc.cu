@@ -576,16 +576,14 @@ extern "C" int pmd_project_stream_tc(const void* movie, int dtype, int64_t t, in
     const int64_t ftiles = (t + 128 * pmd::kPTTiles - 1) / (128 * pmd::kPTTiles);
     PMD_REQUIRE(n_items <= 65535, fn, "too many strip items");
     cudaStream_t st = (cudaStream_t)stream;
-    // profiling aid (results are wrong when set): bit 0 no MMAs, 1 no movie loads, 2 no operand stores, 3 no coefficient copies, 4 no proxy fence
-    static const int ablate = [] {
-        const char* e = getenv("PMD_TC_ABLATE");
-        return e ? atoi(e) : 0;
-    }();
-    // rows of the movie the prefetch warp asks L2 for ahead of the MMA stream (0 = off)
-    static const int pf_rows = [] {
-        const char* e = getenv("PMD_TC_PREFETCH_ROWS");
-        return e ? atoi(e) : 1;   // one row ahead: the strip row of a frame reaches DRAM as one burst (-4 % at C2)
-    }();
+    // Release builds take no switches from the environment.  Development builds (-DPMD_TUNE): PMD_TC_ABLATE is a profiling
+    // aid (results are wrong when set: bit 0 no MMAs, 1 no movie loads, 2 no operand stores, 3 no coefficient copies, 4 no
+    // proxy fence); PMD_TC_PREFETCH_ROWS = rows of the movie the prefetch warp asks L2 for ahead of the MMA stream (0 = off)
+    int ablate = 0, pf_rows = 1;   // one row ahead: the strip row of a frame reaches DRAM as one burst (-4 % at C2)
+#ifdef PMD_TUNE
+    if (const char* e = getenv("PMD_TC_ABLATE")) ablate = atoi(e);
+    if (const char* e = getenv("PMD_TC_PREFETCH_ROWS")) pf_rows = atoi(e);
+#endif
     PMD_DISPATCH_DTYPE(dtype, fn, {
         auto k = pmd::project_tc_kernel<scalar_t>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, pmd::kPTSmem);

@@ -28,6 +28,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -196,7 +197,7 @@ __global__ void __launch_bounds__(kTSThreads, 1)
 project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d2, int64_t d, const TSItem* __restrict__ items,
                   const TSEvent* __restrict__ events, const unsigned char* __restrict__ bimg, const float* __restrict__ mean,
                   float* __restrict__ z, int64_t ldz, float* __restrict__ zbg, int64_t ldzbg, int64_t bg_stride, int n_cols_n,
-                  int tiles, int n_raw) {
+                  int tiles, int n_raw, int movie_policy) {
     using Raw = TSRaw<T>;
     extern __shared__ __align__(1024) unsigned char tssm[];
     __shared__ __align__(8) uint64_t bar_rfull[kTSMaxRaw], bar_rempty[kTSMaxRaw], bar_afull[kTSAStages], bar_aempty[kTSAStages],
@@ -339,9 +340,12 @@ project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d
                                     if (c < nc) {
                                         float* o = zo + (int64_t)c * ldo + f;
                                         const float val = __uint_as_float(v[j][ft][c]);
+                                        // kind 1: only this thread ever touches the element of the strip's partial buffer, and
+                                        // its adds reach the element in program order (deterministic); a reduction instead of
+                                        // load-add-store keeps 32 dependent L2 round trips per batch off the drain's critical path.
+                                        // kind 2: block shared by two strips (z zeroed by the caller)
                                         if (kind == 0) *o = val;
-                                        else if (kind == 1) *o += val;       // this thread owns the element of the strip's partial buffer
-                                        else atomicAdd(o, val);              // block shared by two strips (z zeroed by the caller)
+                                        else atomicAdd(o, val);
                                     }
                                 }
                             }
@@ -494,7 +498,10 @@ project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d
         // ================================ raw movie tiles (one thread) ================================
         if (lane == 0) {
             uint64_t pol_stream;                                                  // the movie is read once: do not let it push the
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol_stream));   // coefficient images out of L2
+            if (movie_policy == 0)                                                // coefficient images out of L2
+                asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol_stream));
+            else
+                asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;\n" : "=l"(pol_stream));
             int rs = 0;
             uint32_t ruse = 0;
             int i = 0;
@@ -643,8 +650,16 @@ static int launch_project_ts(const void* movie, int64_t t, int64_t d2, int64_t d
     cuuint64_t gstr[1] = {(cuuint64_t)d * sizeof(T)};
     cuuint32_t box[2] = {(cuuint32_t)(32 / Raw::kSub), 128u};
     cuuint32_t estr[2] = {1, 1};
+    // 128-byte promotion: a box row is one 128-byte line; with 256 bytes the neighbour strip's half was fetched, evicted (evict_first)
+    // and fetched again (measured at C2: 30.6 GB of DRAM reads and 5.68 ms against 27.4 GB and 5.32 ms)
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+    int movie_policy = 0;
+#ifdef PMD_TUNE   // development builds only: access-shape experiments
+    if (const char* e = getenv("PMD_TS_PROMO")) promo = atoi(e) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : atoi(e) == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : atoi(e) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (const char* e = getenv("PMD_TS_POLICY")) movie_policy = atoi(e);
+#endif
     CUresult r = enc(&tm, dt, 2, const_cast<void*>(movie), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error(std::string(fn) + ": cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
         return -3;
@@ -666,7 +681,7 @@ static int launch_project_ts(const void* movie, int64_t t, int64_t d2, int64_t d
     const int64_t fgroups = (t + 128 * tiles - 1) / (128 * tiles);
     k<<<dim3((unsigned)n_items, (unsigned)fgroups), kTSThreads, smem, st>>>(tm, t, (int)d2, d, (const TSItem*)items, (const TSEvent*)events,
                                                                             (const unsigned char*)bimg, mean, z, ldz, zbg, ldzbg, bg_stride, n,
-                                                                            tiles, n_raw);
+                                                                            tiles, n_raw, movie_policy);
     return check_launch(fn);
 }
 

@@ -273,7 +273,7 @@ int pmd_pack_strips_tc(const int32_t* items, const int32_t* item_of_row, int64_t
  *   - 1 / std folded into the coefficient images (pmd_pack_strips_ts); mean may be NULL.
  * Tables come from pmd_make_strips_ts:
  *   items:  [n_items][12] int32 = (first column c0, 32-pixel chunks per row, first row, rows, first image chunk,
- *           first event, events, bg partial index, first slot_ptr entry, 0, 0, 0)
+ *           first event, events, bg partial index, first slot_ptr entry, 0, n_main = number of full-height items (they come first), 0)
  *   events: [n][4] int32 = (row, slot, first output column, n comps | kind << 8), ascending per item: after that row the
  *           slot is read and cleared; kind 0 stores finished local columns to z, kind 1 ADDS a partial sum of background
  *           columns to zbg (zero on entry), kind 2 atomically ADDS the partial sum of a block shared by two strips to z

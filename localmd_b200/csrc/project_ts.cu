@@ -37,14 +37,14 @@ namespace pmd {
 
 constexpr int kTSBStages = 3;
 constexpr int kTSMaxRaw = 8;                 // raw movie stages (16 KB for float32) kept in flight, as many as fit
-constexpr int kTSEpiWarps = 4, kTSConvGroups = 2, kTSConvWarps = 4 * kTSConvGroups;
+constexpr int kTSEpiWarps = 8, kTSEpiBatch = 8, kTSConvGroups = 2, kTSConvWarps = 4 * kTSConvGroups;
 constexpr int kTSThreads = (kTSEpiWarps + kTSConvWarps + 3) * 32;   // + MMA warp + TMA warp + B loader warp
 constexpr int kTSSmemBudget = 227 * 1024 - 2048;
 constexpr int kTSAccCols = 384, kTSACols = 32;   // tensor memory: accumulators | 4 A stages of 16 pixels (hi 16 + pair 16 columns)
 constexpr int kTSAStages = 4;
 
 struct TSItem {                              // 12 ints (strips_ts_host.cu)
-    int c0, nkc, row0, n_rows, b_chunk0, ev0, n_ev, part, slot_ptr0, n_drain, pad1, pad2;   // n_drain: distinct event rows
+    int c0, nkc, row0, n_rows, b_chunk0, ev0, n_ev, part, slot_ptr0, n_drain, n_main, pad2;   // n_main: full-height items (first in the table)
 };
 struct TSEvent {
     int row, slot, col, ncw;
@@ -69,7 +69,7 @@ __device__ __noinline__ void ts_mbar_wait(uint32_t bar, uint32_t parity) {
             : "memory");
         if (ok) return;
         if (clock64() - t0 > 2000000000ll) {
-            printf("stuck: block (%d,%d) thread %d barrier smem 0x%x parity %u\n", blockIdx.x, blockIdx.y, threadIdx.x, bar, parity);
+            printf("stuck: block (%d,%d) thread %d barrier smem 0x%x parity %u\n", blockIdx.x, 0, threadIdx.x, bar, parity);
             __trap();
         }
     }
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(kTSThreads, 1)
 project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d2, int64_t d, const TSItem* __restrict__ items,
                   const TSEvent* __restrict__ events, const unsigned char* __restrict__ bimg, const float* __restrict__ mean,
                   float* __restrict__ z, int64_t ldz, float* __restrict__ zbg, int64_t ldzbg, int64_t bg_stride, int n_cols_n,
-                  int tiles, int n_raw, int movie_policy) {
+                  int tiles, int n_raw, int movie_policy, int ablate, int n_items_total) {
     using Raw = TSRaw<T>;
     extern __shared__ __align__(1024) unsigned char tssm[];
     __shared__ __align__(8) uint64_t bar_rfull[kTSMaxRaw], bar_rempty[kTSMaxRaw], bar_afull[kTSAStages], bar_aempty[kTSAStages],
@@ -211,8 +211,23 @@ project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d
     const uint32_t sm_base = sr_base + n_raw * Raw::kTile;      // the 32 mean values of every raw stage's pixels (128 bytes each)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // grid: x = strip item (fastest: the CTAs that run together cover whole image rows), y = frame group
-    const TSItem it = items[blockIdx.x];
-    const int64_t f0 = (int64_t)blockIdx.y * (128 * tiles);
+    // 1-D grid.  The n_main full-height items (one per strip) come first, strip index fastest: the CTAs that run together
+    // walk the same image rows of the same frames, so a frame's row reaches DRAM as one burst of neighbouring 128-byte
+    // requests.  The shorter left-over items follow (they would break that lock step) and fill the tail of the grid.
+    int item_idx, fgroup;
+    {
+        const int n_main = items[0].n_main, n_fg = (int)((t + 128 * tiles - 1) / (128 * tiles)), bid = (int)blockIdx.x;
+        if (bid < n_main * n_fg) {
+            item_idx = bid % n_main;
+            fgroup = bid / n_main;
+        } else {
+            const int r = bid - n_main * n_fg, n_extra = n_items_total - n_main;
+            item_idx = n_main + r % n_extra;
+            fgroup = r / n_extra;
+        }
+    }
+    const TSItem it = items[item_idx];
+    const int64_t f0 = (int64_t)fgroup * (128 * tiles);
     const int nft = (int)min((int64_t)tiles, (t - f0 + 127) / 128);   // frame tiles that hold at least one frame
     const int n_groups = it.n_rows * it.nkc;                          // (row, 32-pixel chunk) groups
     const int n_items = n_groups * nft;                               // (group, frame tile) work items
@@ -250,9 +265,11 @@ project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d
 
     if (warp < kTSEpiWarps) {
         // ================================ epilogue warps ================================
-        // warp q reads / writes the tensor-memory lanes 32 q .. 32 q + 31 (= frames of a tile)
-        const uint32_t lane_base = tmem_d + ((uint32_t)(32 * warp) << 16);
-        for (int c = 0; c < kTSAccCols; c += 16) {
+        // warp w reads / writes the tensor-memory lanes 32 (w & 3) .. + 31 (= frames of a tile) of the frame tiles
+        // 2 (w >> 2) and 2 (w >> 2) + 1
+        const int quad = warp & 3, ft0 = 2 * (warp >> 2);
+        const uint32_t lane_base = tmem_d + ((uint32_t)(32 * quad) << 16);
+        for (int c = (warp >> 2) * (kTSAccCols / 2); c < ((warp >> 2) + 1) * (kTSAccCols / 2); c += 16) {
             asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};\n" ::"r"(
                              lane_base + c),
                          "r"(0u)
@@ -262,7 +279,7 @@ project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d
         asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
         ts_mbar_arrive(ts_smem_u32(&bar_accfree));             // completion 0: accumulators are zero
         const int4* ev = reinterpret_cast<const int4*>(events + it.ev0);   // (row, slot, first column, n comps | kind << 8)
-        int e = 0, k = 0;                                       // k = index of the drain row
+        int e = (ablate & 2) ? it.n_ev : 0, k = 0;              // k = index of the drain row
         bool row_open = false;                                  // the accumulators of drain row k are already ours
         while (e < it.n_ev) {
             // Every lane fetches one event of the window [e, e + 32) BEFORE the warp waits for the accumulators (the
@@ -279,70 +296,70 @@ project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
                 row_open = true;
             }
-            for (int eb = 0; eb < cnt; eb += 2) {                // two events (x frame tiles x 4 columns) per batch
-                uint32_t v[2][4][4];
-                int slot[2], colv[2], ncw[2];
+            // The MMA stream stands still until the accumulators are handed back, so a pass first moves up to kTSEpiBatch
+            // finished slots (this warp's two frame tiles of each) into registers and clears them -- back-to-back tensor-
+            // memory instructions, one wait each -- releases the accumulators if these were the row's last events, and
+            // only then forms addresses and issues the global stores / reductions.
+            for (int eb = 0; eb < cnt; eb += kTSEpiBatch) {
+                uint32_t v[kTSEpiBatch][2][4];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    const int src = min(eb + j, 31);
-                    slot[j] = __shfl_sync(0xffffffffu, my.y, src);
-                    colv[j] = __shfl_sync(0xffffffffu, my.z, src);
-                    ncw[j] = __shfl_sync(0xffffffffu, my.w, src);
-                }
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < kTSEpiBatch; ++j) {
                     if (eb + j < cnt) {
-                        const uint32_t ta = lane_base + 4 * slot[j];
+                        const int slot = __shfl_sync(0xffffffffu, my.y, min(eb + j, 31));
+                        const uint32_t ta = lane_base + 4 * slot + N * ft0;
 #pragma unroll
-                        for (int ft = 0; ft < 4; ++ft)
-                            if (ft < nft)
+                        for (int f = 0; f < 2; ++f)
+                            if (ft0 + f < nft)
                                 asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
-                                             : "=r"(v[j][ft][0]), "=r"(v[j][ft][1]), "=r"(v[j][ft][2]), "=r"(v[j][ft][3])
-                                             : "r"(ta + N * ft));
+                                             : "=r"(v[j][f][0]), "=r"(v[j][f][1]), "=r"(v[j][f][2]), "=r"(v[j][f][3])
+                                             : "r"(ta + N * f));
                     }
                 }
                 asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < kTSEpiBatch; ++j) {
                     if (eb + j < cnt) {
-                        const uint32_t ta = lane_base + 4 * slot[j];
+                        const int slot = __shfl_sync(0xffffffffu, my.y, min(eb + j, 31));
+                        const uint32_t ta = lane_base + 4 * slot + N * ft0;
 #pragma unroll
-                        for (int ft = 0; ft < 4; ++ft)
-                            if (ft < nft)
-                                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(ta + N * ft), "r"(0u)
+                        for (int f = 0; f < 2; ++f)
+                            if (ft0 + f < nft)
+                                asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};\n" ::"r"(ta + N * f), "r"(0u)
                                              : "memory");
                     }
                 }
-                if (last_chunk && eb + 2 >= cnt) {               // last batch of this row: hand the accumulators back
+                if (last_chunk && eb + kTSEpiBatch >= cnt) {     // last pass of this row: hand the accumulators back
                     asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
                     ts_mbar_arrive(ts_smem_u32(&bar_accfree));
                 }
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < kTSEpiBatch; ++j) {
                     if (eb + j < cnt) {
-                        const int nc = ncw[j] & 0xFF, kind = ncw[j] >> 8;
+                        const int colv = __shfl_sync(0xffffffffu, my.z, min(eb + j, 31));
+                        const int ncw = __shfl_sync(0xffffffffu, my.w, min(eb + j, 31));
+                        const int nc = ncw & 0xFF, kind = ncw >> 8;
                         float* zo;
                         int64_t ldo;
                         if (kind != 1) {
-                            zo = z + (int64_t)colv[j] * ldz;
+                            zo = z + (int64_t)colv * ldz;
                             ldo = ldz;
                         } else {
-                            zo = zbg + (int64_t)it.part * bg_stride + (int64_t)colv[j] * ldzbg;
+                            zo = zbg + (int64_t)it.part * bg_stride + (int64_t)colv * ldzbg;
                             ldo = ldzbg;
                         }
 #pragma unroll
-                        for (int ft = 0; ft < 4; ++ft) {
-                            const int64_t f = f0 + 128 * ft + 32 * warp + lane;
-                            if (ft < nft && f < t) {
+                        for (int f = 0; f < 2; ++f) {
+                            const int64_t fr = f0 + 128 * (ft0 + f) + 32 * quad + lane;
+                            if (ft0 + f < nft && fr < t && !(ablate & 16)) {
 #pragma unroll
                                 for (int c = 0; c < 4; ++c) {
                                     if (c < nc) {
-                                        float* o = zo + (int64_t)c * ldo + f;
-                                        const float val = __uint_as_float(v[j][ft][c]);
+                                        float* o = zo + (int64_t)c * ldo + fr;
+                                        const float val = __uint_as_float(v[j][f][c]);
                                         // kind 1: only this thread ever touches the element of the strip's partial buffer, and
                                         // its adds reach the element in program order (deterministic); a reduction instead of
-                                        // load-add-store keeps 32 dependent L2 round trips per batch off the drain's critical path.
+                                        // load-add-store keeps dependent L2 round trips out of the drain.
                                         // kind 2: block shared by two strips (z zeroed by the caller)
                                         if (kind == 0) *o = val;
                                         else atomicAdd(o, val);
@@ -371,11 +388,15 @@ project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d
         int rs = j % n_raw;                                                      // raw stage of item i, its use count
         uint32_t ruse = (uint32_t)(j / n_raw);
         for (int i = j, n = 0; i < n_items; i += kTSConvGroups, ++n) {
-            ts_mbar_wait(ts_smem_u32(&bar_rfull[rs]), ruse & 1);
+            if (!(ablate & 8)) ts_mbar_wait(ts_smem_u32(&bar_rfull[rs]), ruse & 1);
             const uint32_t tile = sr_base + rs * Raw::kTile;
             uint32_t hi[32], pr[32];
+            if (ablate & 4) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+                for (int q = 0; q < 32; ++q) hi[q] = pr[q] = (uint32_t)(n + q);
+            }
+#pragma unroll
+            for (int h = 0; h < 2 && !(ablate & 4); ++h) {
                 float x[16];
                 Raw::load16(tile, m, h, x);
                 if (mean) {
@@ -392,7 +413,7 @@ project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d
                     pr[16 * h + q] = ts_pack_bf16(__uint_as_float(hi[16 * h + q]), x[q] - __uint_as_float(hi[16 * h + q]));
                 }
             }
-            ts_mbar_arrive(ts_smem_u32(&bar_rempty[rs]));                        // the raw stage has been read (values are in registers)
+            if (!(ablate & 8)) ts_mbar_arrive(ts_smem_u32(&bar_rempty[rs]));     // the raw stage has been read (values are in registers)
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (n >= 1) {
@@ -462,7 +483,7 @@ project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d
                     if (leader) {
                         const uint32_t a_hi = tmem_d + kTSAccCols + kTSACols * as, a_pr = a_hi + 16;
 #pragma unroll
-                        for (int ks = 0; ks < 2; ++ks) {
+                        for (int ks = 0; ks < 2 && !(ablate & 1); ++ks) {
                             ts_mma_tf32(dcol, a_hi + 8 * ks, desc_hi | (b_tf + 2 * (2 * h + ks)), idesc_tf32);
                             ts_mma_bf16(dcol, a_pr + 8 * ks, desc_hi | (b_bf + 2 * (2 * h + ks)), idesc_bf16);
                         }
@@ -475,7 +496,7 @@ project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d
                 bs = 0;
                 bpar ^= 1;
             }
-            if (kc == it.nkc - 1 && row == next_ev_row) {
+            if (kc == it.nkc - 1 && row == next_ev_row && !(ablate & 2)) {
                 // tasks end at this row: let the epilogue warps drain and clear their slots
                 for (;;) {                                        // skip the events of this row
                     e += __popc(__ballot_sync(0xffffffffu, myrow == row));
@@ -496,7 +517,7 @@ project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t t, int d
         }
     } else if (warp == kTmaWarp) {
         // ================================ raw movie tiles (one thread) ================================
-        if (lane == 0) {
+        if (lane == 0 && !(ablate & 8)) {
             uint64_t pol_stream;                                                  // the movie is read once: do not let it push the
             if (movie_policy == 0)                                                // coefficient images out of L2
                 asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol_stream));
@@ -653,8 +674,9 @@ static int launch_project_ts(const void* movie, int64_t t, int64_t d2, int64_t d
     // 128-byte promotion: a box row is one 128-byte line; with 256 bytes the neighbour strip's half was fetched, evicted (evict_first)
     // and fetched again (measured at C2: 30.6 GB of DRAM reads and 5.68 ms against 27.4 GB and 5.32 ms)
     CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
-    int movie_policy = 0;
-#ifdef PMD_TUNE   // development builds only: access-shape experiments
+    int movie_policy = 0, ablate = 0;   // ablate: profiling aid of -DPMD_TUNE builds (results are wrong when set)
+#ifdef PMD_TUNE
+    if (const char* e = getenv("PMD_TS_ABLATE")) ablate = atoi(e);   // development builds only: access-shape experiments
     if (const char* e = getenv("PMD_TS_PROMO")) promo = atoi(e) == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : atoi(e) == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : atoi(e) == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     if (const char* e = getenv("PMD_TS_POLICY")) movie_policy = atoi(e);
 #endif
@@ -679,9 +701,9 @@ static int launch_project_ts(const void* movie, int64_t t, int64_t d2, int64_t d
         return (int)e;
     }
     const int64_t fgroups = (t + 128 * tiles - 1) / (128 * tiles);
-    k<<<dim3((unsigned)n_items, (unsigned)fgroups), kTSThreads, smem, st>>>(tm, t, (int)d2, d, (const TSItem*)items, (const TSEvent*)events,
+    k<<<dim3((unsigned)(n_items * fgroups)), kTSThreads, smem, st>>>(tm, t, (int)d2, d, (const TSItem*)items, (const TSEvent*)events,
                                                                             (const unsigned char*)bimg, mean, z, ldz, zbg, ldzbg, bg_stride, n,
-                                                                            tiles, n_raw, movie_policy);
+                                                                            tiles, n_raw, movie_policy, ablate, (int)n_items);
     return check_launch(fn);
 }
 
@@ -711,7 +733,7 @@ extern "C" int pmd_project_stream_ts(const void* movie, int dtype, int64_t t, in
     PMD_REQUIRE(d < (1ll << 31) && t < (1ll << 31), fn, "movie too large for 32-bit TMA coordinates");
     PMD_REQUIRE(((uintptr_t)movie & 15) == 0 && ((uintptr_t)bimg & 15) == 0, fn, "movie and image must be 16-byte aligned");
     PMD_REQUIRE(!mean || ((uintptr_t)mean & 15) == 0, fn, "mean must be 16-byte aligned");
-    PMD_REQUIRE(n_items <= 0x7FFFFFFF, fn, "too many strip items");
+    PMD_REQUIRE(n_items * ((t + 255) / 256) <= 0x7FFFFFFF, fn, "too many strip items");
     cudaStream_t st = (cudaStream_t)stream;
     PMD_DISPATCH_DTYPE(dtype, fn, {
         return pmd::launch_project_ts<scalar_t>(movie, t, d2, d, items, n_items, events, bimg, mean, z, ldz, zbg, ldzbg, bg_stride, (int)n,

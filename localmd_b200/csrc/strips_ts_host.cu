@@ -116,7 +116,7 @@ void build(int W, int n_slots, const int32_t* rs, int nbr, const int32_t* cs, in
 
 // Host function (all pointers are HOST pointers).  Outputs (caller allocated):
 //   items    [cap_items][12] int32 = (c0, chunks per row, row0, n_rows, first B chunk, first event, n events,
-//                                    bg partial index, first slot_ptr entry, 0, 0, 0)
+//                                    bg partial index, first slot_ptr entry, 0, n_main (full-height items, first), 0)
 //   slot_ptr [cap_items*49]  int32 : tasks of slot s of item i are slot_ptr[i*49+s] .. slot_ptr[i*49+s+1]-1
 //   tasks    [cap_tasks][8]  int32 = (first row, first column relative to c0 (may be negative), rows, width, first output
 //                                    column, n comps 1..4, kind, 0)
@@ -166,6 +166,8 @@ extern "C" int pmd_make_strips_ts(const int32_t* row_starts, int64_t nbr, const 
         for (int s = 0; s < n_slots; ++s) ntask += (int64_t)it.slots[s].size();
     PMD_REQUIRE((int64_t)best.size() <= cap_items && ntask <= cap_tasks, fn, "output capacity too small");
     int64_t nt = 0, nev = 0, chunks = 0, nparts = 0;
+    int n_main = 0;   // items that span the tallest row range (one per strip when every strip has blocks over its full height)
+    for (const SItem& it : best) n_main += (it.row1 - it.row0) == (best[0].row1 - best[0].row0);
     for (size_t i = 0; i < best.size(); ++i) {
         const SItem& it = best[i];
         int32_t* io = items_out + 12 * i;
@@ -188,21 +190,24 @@ extern "C" int pmd_make_strips_ts(const int32_t* row_starts, int64_t nbr, const 
         for (int s = n_slots; s <= kMaxSlots; ++s) slot_ptr_out[i * (kMaxSlots + 1) + s] = (int32_t)nt;
         // Background tasks accumulate over every row of the strip.  The tensor core adds into its float32 accumulators
         // with truncation, a bias that grows with the number of accumulation steps, so the background slots are
-        // drained (added to the partial sums in float32 by the epilogue) at every row where local tasks end, and at
-        // least every kMaxChain rows.
-        constexpr int kMaxChain = 16;
+        // drained (added to the partial sums in float32 by the epilogue) after at most kMaxChain rows -- at rows where
+        // local tasks end (the MMA stream pauses there anyway) whenever the next such row would be too late.
+        constexpr int kMaxChain = 20;
         drain_rows.push_back(it.row1 - 1);
         std::sort(drain_rows.begin(), drain_rows.end());
         drain_rows.erase(std::unique(drain_rows.begin(), drain_rows.end()), drain_rows.end());
         std::vector<int> bg_rows;
         int last = it.row0 - 1;
-        for (int r : drain_rows) {
-            while (r - last > kMaxChain) {
+        for (size_t q = 0; q < drain_rows.size(); ++q) {
+            const int r = drain_rows[q];
+            while (r - last > kMaxChain) {              // no local task ends in time: a drain of the background alone
                 last += kMaxChain;
                 bg_rows.push_back(last);
             }
-            bg_rows.push_back(r);
-            last = r;
+            if (q + 1 == drain_rows.size() || drain_rows[q + 1] - last > kMaxChain) {
+                bg_rows.push_back(r);
+                last = r;
+            }
         }
         for (int s = 0; s < n_slots; ++s)
             for (const STask& tk : it.slots[s])
@@ -211,7 +216,7 @@ extern "C" int pmd_make_strips_ts(const int32_t* row_starts, int64_t nbr, const 
                         if (r >= tk.by && r < tk.by + tk.h) evs.push_back(Ev{r, s, tk.col, tk.nc | (1 << 8)});
         std::stable_sort(evs.begin(), evs.end(), [](const Ev& a, const Ev& b) { return a.row < b.row; });
         io[0] = it.c0; io[1] = it.nkc; io[2] = it.row0; io[3] = it.row1 - it.row0; io[4] = (int32_t)chunks; io[5] = (int32_t)nev;
-        io[6] = (int32_t)evs.size(); io[7] = it.part; io[8] = (int32_t)(i * (kMaxSlots + 1)); io[9] = io[10] = io[11] = 0;
+        io[6] = (int32_t)evs.size(); io[7] = it.part; io[8] = (int32_t)(i * (kMaxSlots + 1)); io[9] = io[11] = 0; io[10] = n_main;
         PMD_REQUIRE(nev + (int64_t)evs.size() <= cap_events, fn, "event capacity too small");
         for (const Ev& e : evs) {
             int32_t* eo = events_out + 4 * nev++;

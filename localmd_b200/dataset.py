@@ -446,12 +446,14 @@ class DeviceMovie:
                     evs[j] = self._upload(spans[j][0], spans[j][1], self._resident[spans[j][0] - self.lo : spans[j][1] - self.lo])
             self._filled = True
         else:
-            self._copy_stream.wait_stream(cur)
             for f0 in range(self.lo, self.hi, self.upload_frames):
                 f1 = min(self.hi, f0 + self.upload_frames)
+                # the chunk is allocated on the compute stream and written on the copy stream: the copy must not start
+                # before the kernels that used this (recycled) block have run, and the allocator must know both streams
                 chunk = torch.empty((f1 - f0, self.d), dtype=self.torch_dtype, device=self.device)
+                self._copy_stream.wait_stream(cur)
+                chunk.record_stream(self._copy_stream)
                 cur.wait_event(self._upload(f0, f1, chunk))
-                chunk.record_stream(cur)
                 yield f0 - self.lo, chunk
 
     def frame_source(self, global_frame_ids):

@@ -851,13 +851,20 @@ def localmd_decomposition(
     T, d1, d2 = (int(x) for x in dataset_obj.shape)
     d = d1 * d2
     check_fov_size((d1, d2))
+    if group is not None and seed is None:
+        # every rank must draw the same frame lists and sketches (they size the collectives below): rank 0 picks the seed
+        import torch.distributed as dist
+
+        seed_t = torch.tensor([int(np.random.SeedSequence().entropy % (2**62))], dtype=torch.int64, device=dev)
+        dist.broadcast(seed_t, src=dist.get_global_rank(group, 0), group=group)
+        seed = int(seed_t.item())
     rng = np.random.default_rng(seed)
     gen = torch.Generator(device=dev)
     gen.manual_seed(int(rng.integers(0, 2**62)))
     draws = draws if draws is not None else object()
     take = lambda name: getattr(draws, name, None)  # noqa: E731
 
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), ops.fp32_matmul():
         global _ACTIVE_TIMER
         tm = _Timer(timings, dev)
         _ACTIVE_TIMER = tm

@@ -2,8 +2,8 @@
 
 Keys: fov_shape, fov_order, U_data, U_indices, U_indptr, U_shape, U_format, R, s, Vt, mean_img,
 noise_var_img.  The notebook stores U_format = type(U) (a pickled class, hence allow_pickle=True on
-load); here it is stored as the string "csr_matrix" so files load without pickle, and files written by
-the reference's notebook load too (U_format is never read back)."""
+load); here it is stored as the string "csr_matrix"; files are loaded WITHOUT pickle, and files written by
+the reference's notebook load too (U_format is never read back, NpzFile is lazy)."""
 import numpy as np
 import scipy.sparse
 
@@ -30,7 +30,9 @@ def save_npz(path, arr: PMDArray):
 
 
 def load_npz(path, device=None) -> PMDArray:
-    data = np.load(path, allow_pickle=True)
+    # allow_pickle=False: the arrays this loader reads are plain numeric / string arrays also in files written by the
+    # reference's notebook (only its U_format entry is a pickled class, and NpzFile never touches entries not asked for)
+    data = np.load(path, allow_pickle=False)
     u = scipy.sparse.csr_matrix((data["U_data"], data["U_indices"], data["U_indptr"]), shape=tuple(data["U_shape"]))
     v = data["Vt"]
     shape = (v.shape[1], int(data["fov_shape"][0]), int(data["fov_shape"][1]))

@@ -3,6 +3,7 @@
 PyTorch is plumbing only here: it owns device memory and streams; every wrapper validates shapes /
 dtypes / contiguity, allocates outputs and enqueues one kernel (or a short fixed sequence) on the
 current CUDA stream through ctypes.  No wrapper has a CPU path."""
+import contextlib
 import ctypes
 
 import numpy as np
@@ -194,6 +195,20 @@ def _split_tf32(x):
     """x = hi + lo with hi exactly representable in TF32 (10 mantissa bits, round to nearest)."""
     hi = ((x.view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
     return hi, x - hi
+
+
+@contextlib.contextmanager
+def fp32_matmul():
+    """Library GEMMs inside this block run in full float32 whatever the host application set globally
+    (torch.backends.cuda.matmul.allow_tf32 / set_float32_matmul_precision): the parity bars depend on it."""
+    old_tf32, old_prec = torch.backends.cuda.matmul.allow_tf32, torch.get_float32_matmul_precision()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
+    try:
+        yield
+    finally:
+        torch.set_float32_matmul_precision(old_prec)
+        torch.backends.cuda.matmul.allow_tf32 = old_tf32
 
 
 def matmul_3xtf32(a, b):

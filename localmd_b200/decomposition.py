@@ -100,6 +100,16 @@ def identify_window_chunks(frame_range, total_frames, window_chunks, rng, starti
 
 
 _ACTIVE_TIMER = None
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev, priority=0):
+    """One cached side stream per (device, priority): the caching allocator keeps a pool per stream, so a fresh stream per
+    call would cudaMalloc (and synchronise) every time."""
+    key = (str(dev), priority)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev, priority=priority)
+    return _SIDE_STREAMS[key]
 
 
 def _submark(name):
@@ -201,9 +211,10 @@ def background_basis(movie: DeviceMovie, mean, std, bg_frames, bg_sketch, backgr
     return u.t().contiguous()
 
 
-def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, chunk=None):
+def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, chunk=None, defer=False):
     """decomposition.py:147-189: roughness statistics of the rank-1 rSVD of pure-noise blocks.
-    Every simulated block is its own tiny pixel-major movie (b, ld) for the block kernels."""
+    Every simulated block is its own tiny pixel-major movie (b, ld) for the block kernels.
+    defer=True: the device work is only enqueued; the returned callable fetches the statistics and takes the percentiles."""
     b = bh * bw
     ld = (t_win + 3) // 4 * 4
     if chunk is None:   # as many simulated blocks per batch as ~3 GB of noise allow (all 250 at C2: fewer, larger launches)
@@ -240,9 +251,12 @@ def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, 
         ss, ts, _ = ops.block_stats_rank(u1, v1, bh, bw, 1, float("inf"), float("inf"), 1, t=t_win)
         sp.append(ss.reshape(-1))
         tp.append(ts.reshape(-1))
-    sp = torch.cat(sp).cpu().numpy()
-    tp = torch.cat(tp).cpu().numpy()
-    return np.percentile(sp.flatten(), sim_conf), np.percentile(tp.flatten(), sim_conf)
+    sp, tp = torch.cat(sp), torch.cat(tp)
+
+    def finish():
+        return np.percentile(sp.cpu().numpy().flatten(), sim_conf), np.percentile(tp.cpu().numpy().flatten(), sim_conf)
+
+    return finish if defer else finish()
 
 
 def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_t, mcf, sketches, spatial_denoiser=None,
@@ -888,6 +902,21 @@ def localmd_decomposition(
             bounds = [(int(b[0]), int(b[1])) for b in torch.stack(allb).cpu()]
         tm.mark("upload")
 
+        # ---- thresholds (decomposition.py:706-711), enqueued early on a high-priority side stream ------------------
+        # The simulation only depends on the block geometry: its ~4 ms of small launches run beside the statistics pass.
+        wc_eff = frame_range if window_chunks is None else window_chunks
+        fr_eff = min(frame_range, T)
+        wc_eff = fr_eff if fr_eff <= wc_eff else wc_eff
+        bh_e, bw_e = (min(int(b_), int(n_)) for b_, n_ in zip(block_sizes, (d1, d2)))
+        thr_pending = None
+        if take("thresholds") is None and min(bh_e, bw_e) >= 10:
+            side_thr = _side_stream(dev, -1)
+            side_thr.wait_stream(torch.cuda.current_stream(dev))
+            gen_sim = torch.Generator(device=dev)
+            gen_sim.manual_seed(gen.initial_seed() + 1)
+            with torch.cuda.stream(side_thr):
+                thr_pending = (simulate_thresholds(bh_e, bw_e, wc_eff, sim_conf, draws, gen_sim, dev, defer=True), bh_e, bw_e, wc_eff)
+
         # ---- PMDLoader.__init__ : normalisers + background (pmd_loader.py:172-173) --------------
         say("Computing Video Statistics")
         mean, std = compute_mean_and_noise(movie, compute_normalizer, group)
@@ -935,6 +964,9 @@ def localmd_decomposition(
         thr = take("thresholds")
         if thr is not None:
             thr_s, thr_t = float(thr[0]), float(thr[1])
+        elif thr_pending is not None and thr_pending[1:] == (bh, bw, window_chunks):
+            torch.cuda.current_stream(dev).wait_stream(side_thr)
+            thr_s, thr_t = thr_pending[0]()
         else:
             thr_s, thr_t = simulate_thresholds(bh, bw, window_chunks, sim_conf, draws, gen, dev)
         tm.mark("thresholds")
@@ -1076,6 +1108,19 @@ def localmd_decomposition(
         v_full = project_movie(movie, su, p, mean, inv_std)
         tm.mark("projection")
 
+        # ---- result CSR on a side stream -------------------------------------------------------------
+        # The relabelled CSR of U (sorts / scatters, ~3.4 ms at C2) only depends on the assembled components: it runs
+        # beside the final SVD, whose float64 eigensolver leaves most of the GPU idle.
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        side.wait_stream(main)
+        row_ids = torch.from_numpy(np.arange(d).reshape((d1, d2), order=order).reshape(-1)).to(dev)
+        with torch.cuda.stream(side):
+            indptr, indices, values = su.csr(row_ids)
+            csr32 = su.csr_physical32()
+        for t_ in (indptr, indices, values) + tuple(csr32):
+            t_.record_stream(main)
+
         # ---- final SVD (decomposition.py:896-904) ---------------------------------------------------
         rmix, s, vt = projected_svd(p, v_full, group)
         good = s != 0
@@ -1086,10 +1131,8 @@ def localmd_decomposition(
         tm.mark("final_svd")
 
         # ---- result object ---------------------------------------------------------------------------
-        row_ids = torch.from_numpy(np.arange(d).reshape((d1, d2), order=order).reshape(-1)).to(dev)
-        indptr, indices, values = su.csr(row_ids)
-        _submark("export.csr")
-        out = PMDArray._from_device((indptr, indices, values), su.csr_physical32(), rmix.contiguous(), s.contiguous(),
+        main.wait_stream(side)
+        out = PMDArray._from_device((indptr, indices, values), csr32, rmix.contiguous(), s.contiguous(),
                                     vt.contiguous(), (T, d1, d2), order, mean, std, dev)
         tm.mark("export")
         tm.finish()

@@ -138,14 +138,28 @@ extern "C" int pmd_make_strips_ts(const int32_t* row_starts, int64_t nbr, const 
     std::vector<SItem> best, cur;
     double best_cost = -1, cost = 0;
     int best_w = 0, best_n = 0;
+    // Candidates: the two narrowest strip widths a block fits in (wider strips multiply every 32-pixel chunk with more
+    // slot columns that are zero for it), and slot counts in ascending order until one packs every task into the
+    // full-height items (more slots then only cost tensor time).
     for (int N : {96, 128, 192}) {
         if (n_fixed > 0 && N != n_fixed) continue;
         if ((n_bg + kSlotCols - 1) / kSlotCols >= N / kSlotCols) continue;   // the background alone fills the slots
+        if (best_cost >= 0 && n_fixed <= 0) {
+            // lower bound of this N: every image row of every 32-pixel chunk exactly once, no left-over items
+            const int tiles = 384 / N;
+            const double per = std::max(730.0, 4.0 * N + 100.0) + (2.0 * N * 128 / 40.0) / tiles;
+            if (per * (double)d1 * (double)((d2 + 31) / 32) >= best_cost) break;
+        }
+        int tried = 0;
+        bool all_fit = false;
         for (int W : {32, 64, 96, 128}) {
             if (w_fixed > 0 && W != w_fixed) continue;
             if (bw - 1 > W) continue;
+            if (w_fixed <= 0 && tried >= 2) break;
+            ++tried;
             build(W, N / kSlotCols, row_starts, (int)nbr, col_starts, (int)nbc, (int)bh, (int)bw, (int)d1, (int)d2, ranks, col0,
                   (int)n_bg, cur, cost);
+            if (tried == 1 && (int64_t)cur.size() * W >= d2 && (int64_t)(cur.size() - 1) * W < d2) all_fit = true;
             if (best_cost < 0 || cost < best_cost) {
                 best_cost = cost;
                 best_w = W;
@@ -153,6 +167,7 @@ extern "C" int pmd_make_strips_ts(const int32_t* row_starts, int64_t nbr, const 
                 best.swap(cur);
             }
         }
+        if (all_fit && n_fixed <= 0) break;
     }
     if (best_cost < 0) return 0;
     const int n_slots = best_n / kSlotCols;

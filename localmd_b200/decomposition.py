@@ -11,6 +11,7 @@ Same signature, defaults, guards and result object as the reference.  Extra keyw
   details    dict filled with intermediates (ranks, thresholds, background basis, ...) for tests.
 README aliases block_height/block_width/frames_to_init are accepted.
 """
+import concurrent.futures
 import datetime
 import math
 import os
@@ -101,6 +102,7 @@ def identify_window_chunks(frame_range, total_frames, window_chunks, rng, starti
 
 _ACTIVE_TIMER = None
 _SIDE_STREAMS = {}
+_HOST_POOL = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="pmd-host-tables")
 
 
 def _side_stream(dev, priority=0):
@@ -507,11 +509,15 @@ class SparseU:
         self._regular = (rows, cols) if regular else None
         self._tc_host = None
         self._ts_host = None
+        self._ts_future = None
         which = os.environ.get("PMD_K7", "ts")   # development switch between the generations of the projection kernel
         if regular and which == "ts":
             # K7 with TMA-fed raw tiles and the movie operand in tensor memory (csrc/project_ts.cu): host tables now
             # (native library), device tables and coefficient images at the first projection call
-            self._ts_host = ops.make_strips_ts(rows, cols, bh, bw, d1, d2, ranks_host, self.col0_host, bg.shape[0])
+            # the native routine releases the GIL: it runs on a worker thread while this thread enqueues the whitening
+            self._ts_future = _HOST_POOL.submit(ops.make_strips_ts, rows, cols, bh, bw, d1, d2, ranks_host.copy(), self.col0_host.copy(),
+                                                bg.shape[0])
+            self._ts_host = True   # placeholder until the first projection call collects the result
         if regular and self._ts_host is None and which != "simt":
             # K7 on the tensor cores (csrc/project_tc.cu): host tables now (native library), device tables and
             # coefficient images at the first projection call
@@ -544,6 +550,9 @@ class SparseU:
     def _finish_ts(self, inv_std):
         """Upload the tables of the TMA / tensor-memory kernel and build its coefficient images with 1 / std folded in
         (once per decomposition, at the first projection call)."""
+        if self._ts_future is not None:
+            self._ts_host = self._ts_future.result()
+            self._ts_future = None
         st = self._ts_host
         if st is not None:
             self._ts_host = None
@@ -669,6 +678,17 @@ class SparseU:
     def project(self, movie2d, mean, inv_std, z):
         """z[:, :n] (R, ldz) (+)= U^T standardised(movie2d)   (K7a + K7b)."""
         n = movie2d.shape[0]
+        if self._ts_future is not None:
+            self._ts_host = self._ts_future.result()
+            self._ts_future = None
+            if self._ts_host is None and self._regular is not None:   # geometry the TMA kernel does not take: older kernels
+                rows, cols = self._regular
+                self._tc_host = ops.make_strips_tc(rows, cols, self.bh, self.bw, self.d1, self.d2, self.ranks_host, self.col0_host,
+                                                   self.bg.shape[0])
+                if self._tc_host is None:
+                    self._build_simt_strips()
+                if self.strips is None and self._tc_host is None:
+                    self._build_supertiles()
         if (self._ts_host is not None or self.strips_ts is not None) and ops.project_stream_ts_ok(movie2d, self.d2, mean):
             self._finish_ts(inv_std)
             ops.project_stream_ts(movie2d, self.d2, self.strips_ts, self.bimg_ts, mean, z[: self.n_local], z[self.n_local :])

@@ -47,6 +47,17 @@ int pmd_abi_version(void);
 int pmd_stats_pass(const void* movie, int dtype, int64_t t_local, int64_t d, int64_t t_total, const float* tab,
                    float* mean_part, float* noise_part, void* stream);
 
+/* K1 on the tensor cores (csrc/stats_tc.cu): same contract and outputs as pmd_stats_pass, for movies whose frame pitch
+ * d * sizeof(element) is a multiple of 16 bytes and whose base address is 16-byte aligned (2-D TMA boxes of 16 frames x
+ * 128 pixels).  The segment transform runs as TF32 + bf16-pair tcgen05 MMAs on the radix-2 decimation-in-frequency form
+ * (even bins from w x[t] + (1 - w) x[t + 128], odd bins from w x[t] - (1 - w) x[t + 128]) against two constant (64 x 128)
+ * matrices.  tab: 131584 bytes built by the host (localmd_b200/_tables.py: welch_tc_tables): the matrices in the
+ * shared-memory operand layout (TF32 parts, then bf16 pair parts; K-major SWIZZLE_128B) and the first half of the
+ * periodic Hann window as float32.
+ * replaces: pmd_loader.py:203-291 and preprocessing_utils.py:10-40 (as pmd_stats_pass). */
+int pmd_stats_pass_tc(const void* movie, int dtype, int64_t t_local, int64_t d, int64_t t_total, const void* tab,
+                      float* mean_part, float* noise_part, void* stream);
+
 /* gather + standardise frames: out[i][p] = (movie[frames[i]][p] - mean[p]) / stdv[p]  (float32).
  * replaces: pmd_loader.py:293-298 (temporal_crop_standardized) and the first two lines of
  *           standardize_and_filter, pmd_loader.py:374-377. */

@@ -4,13 +4,14 @@ PyTorch is plumbing only here: it owns device memory and streams; every wrapper 
 dtypes / contiguity, allocates outputs and enqueues one kernel (or a short fixed sequence) on the
 current CUDA stream through ctypes.  No wrapper has a CPU path."""
 import contextlib
+import os
 import ctypes
 
 import numpy as np
 import torch
 
 from . import _lib
-from ._tables import welch_fft_tables
+from ._tables import welch_fft_tables, welch_tc_tables
 
 PMD_DTYPES = {
     torch.float32: 0,
@@ -69,6 +70,13 @@ def _tables(device):
     return _table_cache[key]
 
 
+def _tables_tc(device):
+    key = "tc:" + str(device)
+    if key not in _table_cache:
+        _table_cache[key] = torch.from_numpy(welch_tc_tables()).to(device)
+    return _table_cache[key]
+
+
 def movie_dtype_code(t):
     if t.dtype not in PMD_DTYPES:
         raise TypeError("unsupported movie dtype %s" % t.dtype)
@@ -84,9 +92,14 @@ def stats_pass(movie2d, t_total):
     n_chunks = (t_local + 1023) // 1024
     mean_part = torch.empty((n_chunks, d), dtype=torch.float32, device=movie2d.device)
     noise_part = torch.empty((n_chunks, d), dtype=torch.float32, device=movie2d.device)
-    tab = _tables(movie2d.device)
-    _call("pmd_stats_pass", _p(movie2d), movie_dtype_code(movie2d), t_local, d, t_total, _p(tab), _p(mean_part),
-          _p(noise_part), _stream())
+    which = os.environ.get("PMD_K1", "tc")   # development switch between the generations of the statistics kernel
+    if which == "tc" and movie2d.data_ptr() % 16 == 0 and (d * movie2d.element_size()) % 16 == 0:
+        # K1 on the tensor cores (csrc/stats_tc.cu): 2-D TMA boxes need 16-byte aligned frames
+        _call("pmd_stats_pass_tc", _p(movie2d), movie_dtype_code(movie2d), t_local, d, t_total, _p(_tables_tc(movie2d.device)),
+              _p(mean_part), _p(noise_part), _stream())
+    else:
+        _call("pmd_stats_pass", _p(movie2d), movie_dtype_code(movie2d), t_local, d, t_total, _p(_tables(movie2d.device)),
+              _p(mean_part), _p(noise_part), _stream())
     n_var = sum(1 for c in range(n_chunks) if min(1024, t_local - 1024 * c) >= 256)
     return mean_part, noise_part, n_var
 

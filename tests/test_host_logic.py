@@ -99,6 +99,33 @@ def test_welch_tables_identity():
         np.testing.assert_allclose(welch_fft_reference(x), O.welch_noise_estimate(x), rtol=1e-6)
 
 
+def test_welch_tc_tables():
+    """The decimation-in-frequency form the tensor-core stats kernel evaluates equals scipy's welch, and the operand image
+    decodes (TF32 part + bf16 pair part, swizzled K-major layout) back to the two DFT matrices."""
+    from localmd_b200._tables import welch_dif_matrices, welch_dif_reference, welch_tc_tables
+
+    rng = np.random.default_rng(1)
+    for n in (1024, 544, 256, 300):
+        x = (200 + 3 * rng.standard_normal((16, n)) + 0.02 * np.arange(n)).astype(np.float32)
+        np.testing.assert_allclose(welch_dif_reference(x), O.welch_noise_estimate(x), rtol=1e-6)
+    tab = welch_tc_tables()
+    assert tab.dtype == np.uint8 and tab.shape == (131072 + 512,)
+    words = tab[:131072].view(np.uint32)
+    w = tab[131072:].view(np.float32)
+    np.testing.assert_allclose(w, 0.5 - 0.5 * np.cos(2 * np.pi * np.arange(128) / 256), rtol=1e-6, atol=1e-8)
+    for par, mat in enumerate(welch_dif_matrices()):
+        for n_, k_ in ((0, 0), (5, 37), (63, 127), (17, 64), (40, 95)):
+            ka, kk = k_ // 32, k_ % 32
+            off = ka * 8192 + (n_ >> 3) * 1024 + (n_ & 7) * 128 + (((kk // 4) ^ (n_ & 7)) << 4) + 4 * (kk % 4)
+            hi = words[par * 8192 + off // 4 : par * 8192 + off // 4 + 1].view(np.float32)[0]
+            pair = int(words[16384 + par * 8192 + off // 4])
+            lo = np.array([(pair & 0xFFFF) << 16], np.uint32).view(np.float32)[0]
+            hi_b = np.array([pair & 0xFFFF0000], np.uint32).view(np.float32)[0]
+            assert (np.float32(hi).view(np.uint32) & 0x1FFF) == 0                      # exact in TF32
+            assert abs(float(hi) + float(lo) - mat[n_, k_]) <= 2.0 ** -17 * max(abs(mat[n_, k_]), 1e-3)
+            assert abs(float(hi_b) - float(hi)) <= 2.0 ** -8 * abs(float(hi)) + 1e-30
+
+
 def test_npz_layout_and_pmdarray_container():
     import localmd_b200
 

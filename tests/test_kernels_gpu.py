@@ -49,6 +49,37 @@ def test_stats_pass(ops, T, d1, d2, dtype):
         assert n_var == 0 and float(npart.abs().max()) == 0.0
 
 
+@pytest.mark.parametrize(
+    "T,d1,d2,dtype",
+    [(1024, 8, 16, np.float32), (2048 + 544, 13, 12, np.float32), (700, 16, 24, np.uint16), (256, 4, 4, np.float32),
+     (300, 16, 9, np.float32), (1500, 16, 16, np.int16), (100, 8, 8, np.float32), (3000, 40, 36, np.uint8),
+     (1300, 12, 10, np.float64), (1024 + 255, 20, 20, np.int32), (4096 + 130, 64, 66, np.float32)],
+)
+@pytest.mark.parametrize("which", ["tc", "fft"])
+def test_stats_pass_both_kernels(ops, T, d1, d2, dtype, which, monkeypatch):
+    """Both generations of K1 (tensor-core DFT behind 2-D TMA, and the SIMT FFT kernel the unaligned movies fall back to)
+    against the oracle's mean / Welch estimate; includes a movie with strong slow signals (rounding of the DFT matrix)."""
+    monkeypatch.setenv("PMD_K1", which)
+    rng = np.random.default_rng(T + d1)
+    base = rng.uniform(50, 200, size=(d1, d2))
+    sig = rng.uniform(0.5, 4, size=(d1, d2))
+    tt = np.arange(T)
+    slow = 40.0 * np.exp(-((tt - 100) % 300) / 15.0)[:, None, None] * rng.uniform(0, 1, size=(1, d1, d2)) + 0.01 * tt[:, None, None]
+    y = base[None] + sig[None] * rng.standard_normal((T, d1, d2)) + slow
+    if np.issubdtype(dtype, np.integer):
+        y = np.clip(np.rint(y), 0, np.iinfo(dtype).max)
+    movie = y.astype(dtype)
+    mean_ref, std_ref = O.mean_and_noise(movie)
+    mp, npart, n_var = ops.stats_pass(dev(movie).view(T, d1 * d2), T)
+    mean = mp.sum(0).cpu().numpy().reshape(d1, d2)
+    np.testing.assert_allclose(mean, mean_ref, rtol=2e-6)
+    if T >= 256:
+        std = (npart.sum(0) / n_var).cpu().numpy().reshape(d1, d2)
+        np.testing.assert_allclose(std, std_ref, rtol=2e-5)
+    else:
+        assert n_var == 0 and float(npart.abs().max()) == 0.0
+
+
 def test_standardize_frames(ops):
     rng = np.random.default_rng(1)
     movie = rng.integers(0, 4000, size=(40, 37)).astype(np.uint16)

@@ -134,6 +134,41 @@ __device__ __forceinline__ void st_sttm16(uint32_t addr, const uint32_t (&v)[16]
         : "memory");
 }
 
+// packed float32 pairs (FADD2 / FMUL2 of sm_100): half the issue slots of the conversion arithmetic
+__device__ __forceinline__ uint64_t st_pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void st_unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;\n" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t st_add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;\n" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t st_sub2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("sub.rn.f32x2 %0, %1, %2;\n" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t st_mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;\n" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// x -> (TF32-exact hi, bf16 pair (bf16(hi), bf16(x - hi))) for both halves of a packed pair
+__device__ __forceinline__ void st_split2(uint64_t x2, uint32_t& hi0, uint32_t& hi1, uint32_t& pr0, uint32_t& pr1) {
+    float x0, x1, l0, l1;
+    st_unpack2(x2, x0, x1);
+    hi0 = __float_as_uint(x0) & 0xFFFFE000u;
+    hi1 = __float_as_uint(x1) & 0xFFFFE000u;
+    st_unpack2(st_sub2(x2, st_pack2(__uint_as_float(hi0), __uint_as_float(hi1))), l0, l1);
+    pr0 = st_pack_bf16(__uint_as_float(hi0), l0);
+    pr1 = st_pack_bf16(__uint_as_float(hi1), l1);
+}
+
 struct STUnit {
     int chunk, x0, n, nst, nseg;
     int64_t f_begin;
@@ -215,9 +250,17 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap tm_movie, const T* __restric
             st_mbar_wait(st_smem_u32(&bar_c0full[cb]), (ucnt >> 1) & 1);
             const float c0 = valid ? to_f32(c0buf[cb * (1024 / (int)sizeof(T)) + m]) : 0.f;
             st_mbar_arrive(st_smem_u32(&bar_c0empty[cb]));
-            float msum = 0.f, pw = 0.f;
+            uint64_t msum2 = 0ull;                                    // packed partial sums of (x - c0)
+            float pw = 0.f;
             int cnt = 0, seg_read = 0;
-            float p[4][16];                                           // w * (x - c0) of this thread's stages of the previous hop block
+            uint64_t p[4][8];                                         // w * (x - c0) of this thread's stages of the previous hop block
+            const uint64_t c02 = st_pack2(c0, c0);
+            int slot, use;                                            // raw stage of this thread's next stage (advances by 2)
+            {
+                const int sg0 = s_base + g;
+                use = sg0 / n_raw;
+                slot = sg0 - use * n_raw;
+            }
             // sum of squares of this group's half (even bins: group 0, odd bins: group 1) of a finished segment
             auto read_segment = [&](int sidx) {
                 const int segc = seg_base + sidx, buf = segc & 1;
@@ -253,45 +296,54 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap tm_movie, const T* __restric
                 for (int jj = 0; jj < 4; ++jj) {
                     const int j = 2 * jj + g, st = blk * 8 + j;
                     if (st < u.nst) {
-                        const int sg = s_base + st, slot = sg % n_raw, use = sg / n_raw;
                         st_mbar_wait(st_smem_u32(&bar_rfull[slot]), use & 1);
                         const T* src = ring + (size_t)slot * (kSTStage * kSTPix) + m;
                         const int left = u.n - kSTStage * st;          // frames of this stage inside the chunk
-                        float xv[16];
+                        uint64_t xv[8];
+                        // (pixels beyond the field of view read the zero fill of the TMA box and have c0 = 0)
+                        if (left >= 16) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) xv[i] = (valid && i < left) ? to_f32(src[i * kSTPix]) - c0 : 0.f;
+                            for (int i = 0; i < 8; ++i)
+                                xv[i] = st_sub2(st_pack2(to_f32(src[2 * i * kSTPix]), to_f32(src[(2 * i + 1) * kSTPix])), c02);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i)
+                                xv[i] = st_pack2(2 * i < left ? to_f32(src[2 * i * kSTPix]) - c0 : 0.f,
+                                                 2 * i + 1 < left ? to_f32(src[(2 * i + 1) * kSTPix]) - c0 : 0.f);
+                        }
                         st_mbar_arrive(st_smem_u32(&bar_rempty[slot]));   // values are in registers
+                        slot += 2;
+                        if (slot >= n_raw) {
+                            slot -= n_raw;
+                            ++use;
+                        }
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) msum += xv[i];
+                        for (int i = 0; i < 8; ++i) msum2 = st_add2(msum2, xv[i]);
                         cnt += min(left, 16);
-                        const float4* w4 = reinterpret_cast<const float4*>(wtab + 16 * j);
+                        const ulonglong2* w2 = reinterpret_cast<const ulonglong2*>(wtab + 16 * j);
                         if (!mma) {
                             if (blk == 0) {
 #pragma unroll
                                 for (int i4 = 0; i4 < 4; ++i4) {
-                                    const float4 w = w4[i4];
-                                    p[jj][4 * i4] = w.x * xv[4 * i4];
-                                    p[jj][4 * i4 + 1] = w.y * xv[4 * i4 + 1];
-                                    p[jj][4 * i4 + 2] = w.z * xv[4 * i4 + 2];
-                                    p[jj][4 * i4 + 3] = w.w * xv[4 * i4 + 3];
+                                    const ulonglong2 w = w2[i4];
+                                    p[jj][2 * i4] = st_mul2(w.x, xv[2 * i4]);
+                                    p[jj][2 * i4 + 1] = st_mul2(w.y, xv[2 * i4 + 1]);
                                 }
                             }
                         } else {
-                            float bb[16];
+                            uint64_t bb[8];
                             uint32_t hi[16], pr[16];
 #pragma unroll
                             for (int i4 = 0; i4 < 4; ++i4) {
-                                const float4 w = w4[i4];
-                                const float wv[4] = {w.x, w.y, w.z, w.w};
+                                const ulonglong2 w = w2[i4];
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) {
-                                    const int i = 4 * i4 + e;
-                                    const float pn = wv[e] * xv[i], q = xv[i] - pn;     // w x and (1 - w) x of the new hop block
-                                    const float a = p[jj][i] + q;
-                                    bb[i] = p[jj][i] - q;
+                                for (int e = 0; e < 2; ++e) {
+                                    const int i = 2 * i4 + e;
+                                    const uint64_t pn = st_mul2(e ? w.y : w.x, xv[i]), q = st_sub2(xv[i], pn);   // w x, (1 - w) x
+                                    const uint64_t a = st_add2(p[jj][i], q);
+                                    bb[i] = st_sub2(p[jj][i], q);
                                     p[jj][i] = pn;
-                                    hi[i] = __float_as_uint(a) & 0xFFFFE000u;
-                                    pr[i] = st_pack_bf16(__uint_as_float(hi[i]), a - __uint_as_float(hi[i]));
+                                    st_split2(a, hi[2 * i], hi[2 * i + 1], pr[2 * i], pr[2 * i + 1]);
                                 }
                             }
                             const int qa = q_base + (blk - 1) * 8 + j, as = qa & (kSTAStages - 1), ause = qa >> 2;
@@ -303,10 +355,7 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap tm_movie, const T* __restric
                             st_sttm16(ta, hi);
                             st_sttm16(ta + 16, pr);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) {
-                                hi[i] = __float_as_uint(bb[i]) & 0xFFFFE000u;
-                                pr[i] = st_pack_bf16(__uint_as_float(hi[i]), bb[i] - __uint_as_float(hi[i]));
-                            }
+                            for (int i = 0; i < 8; ++i) st_split2(bb[i], hi[2 * i], hi[2 * i + 1], pr[2 * i], pr[2 * i + 1]);
                             st_sttm16(ta + 32, hi);
                             st_sttm16(ta + 48, pr);
                             asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
@@ -323,6 +372,9 @@ stats_tc_kernel(const __grid_constant__ CUtensorMap tm_movie, const T* __restric
             q_base += 8 * u.nseg;
             seg_base += u.nseg;
             // group 1 hands its partial sums to group 0, which writes the unit's results
+            float msum_lo, msum_hi;
+            st_unpack2(msum2, msum_lo, msum_hi);
+            const float msum = msum_lo + msum_hi;
             if (g == 1) {
                 if (ucnt >= 1) st_mbar_wait(st_smem_u32(&bar_mempty), (ucnt - 1) & 1);
                 msum_s[m] = (double)c0 * (double)cnt + (double)msum;

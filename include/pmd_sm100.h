@@ -151,6 +151,17 @@ int pmd_block_project_tc(const float* movie_t, int64_t movie_batch_stride, int64
                          const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* w_hi,
                          const float* w_lo, int64_t r, int64_t rp, float* out, int64_t ldo, void* stream);
 
+/* the block projection with the movie operand in tensor memory (csrc/blocks_ts.cu): raw [32 pixels x 128 frames] tiles
+ * by 2-D TMA boxes, split in registers and written to tensor memory (tcgen05.st), TF32 + bf16-pair MMAs (float32-class
+ * accuracy), persistent CTAs with double-buffered accumulators.  w: [nb][bh*bw][rp] float32 (unsplit; rp <= 64);
+ * workspace: pmd_block_project_ts_workspace_bytes(nb, bh, bw) bytes of device memory for the packed coefficient
+ * images (16-byte aligned); n_rows: number of pixel rows of movie_t (all batches); movie_batch_stride must be a multiple
+ * of ld; bw even.  Same outputs as pmd_block_project. */
+int64_t pmd_block_project_ts_workspace_bytes(int64_t nb, int64_t bh, int64_t bw);
+int pmd_block_project_ts(const float* movie_t, int64_t movie_batch_stride, int64_t n_rows, int64_t ld, int64_t d2,
+                         const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* w, int64_t r, int64_t rp,
+                         void* workspace, float* out, int64_t ldo, void* stream);
+
 /* streaming spatial projection  s[b][q][c] = sum_f Y_b[q][f] * v[b][c][f]   (all ldv frames of v).
  * replaces: decomposition.py:304-306 (block * v_basis^T).   v: [nb][r][ldv] (ldv multiple of 4, padding
  * zero); s: [nb][bh*bw][rp], rp <= 64. */

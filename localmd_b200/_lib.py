@@ -62,6 +62,8 @@ def lib():
         L.pmd_last_error.restype = ctypes.c_char_p
         L.pmd_last_error.argtypes = []
         L.pmd_abi_version.restype = c_int
+        L.pmd_block_project_ts_workspace_bytes.restype = c_i64   # the one entry point that returns a size, not a status
+        L.pmd_block_project_ts_workspace_bytes.argtypes = [c_i64, c_i64, c_i64]
         for name, sig in _parse_header().items():
             fn = getattr(L, name)
             fn.restype = c_int

@@ -333,8 +333,22 @@ def block_project_tc(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, w, r, 
     nb, bpix, rp = w.shape
     assert bpix == bh * bw and starts.shape[0] == nb and rp <= 64
     ldo = ld if ldo is None else int(ldo)
-    w_hi, w_lo = _split_tf32(w)
     out = torch.empty((nb, r, ldo), dtype=torch.float32, device=movie_t.device)
+    which = os.environ.get("PMD_BLOCK_PROJECT", "ts")   # development switch between the generations of the kernel
+    n_rows = movie_t.numel() // ld
+    if (which == "ts" and bw % 2 == 0 and movie_batch_stride % ld == 0 and movie_t.data_ptr() % 16 == 0 and movie_t.is_contiguous()
+            and n_rows < 2**31):
+        # movie operand in tensor memory (csrc/blocks_ts.cu)
+        wc = w.contiguous()
+        step = 65535
+        for s in range(0, nb, step):
+            m = min(step, nb - s)
+            ws = torch.empty(int(_lib.lib().pmd_block_project_ts_workspace_bytes(m, bh, bw)), dtype=torch.uint8, device=movie_t.device)
+            mv = ctypes.c_void_p(movie_t.data_ptr() + 4 * s * movie_batch_stride)
+            _call("pmd_block_project_ts", mv, movie_batch_stride, n_rows - s * (movie_batch_stride // ld), ld, d2, _p(starts[s:]), m, bh, bw,
+                  _p(wc[s:]), r, rp, _p(ws), _p(out[s:]), ldo, _stream())
+        return out
+    w_hi, w_lo = _split_tf32(w)
     step = 65535
     for s in range(0, nb, step):
         m = min(step, nb - s)

@@ -1,10 +1,13 @@
-"""Block-stage contraction micro-benchmark: SIMT vs tcgen05 block projection at C2 (2601 blocks of 20x20, t=5000, r=50)."""
+"""Block-stage contraction micro-benchmark at C2 (2601 blocks of 20x20, t=5000, r=50): the generations of the block
+projection (tcgen05 with the movie operand staged in shared memory / in tensor memory) and the spatial projection.
+Usage: python scripts/bench_blocks.py [project|spatial|all]"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from localmd_b200 import ops
 from localmd_b200.decomposition import tile_starts
+which = sys.argv[1] if len(sys.argv) > 1 else "all"
 d1 = d2 = 512; bh = bw = 20; t = 5000; r = 50; rp = 52
 dev = torch.device("cuda")
 rows, cols = tile_starts(d1, bh), tile_starts(d2, bw)
@@ -20,12 +23,14 @@ def timeit(name, fn, reps=3):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     fl = 2.0 * nb * bh * bw * r * t
-    print("%-22s %7.2f ms  %6.1f TFLOP/s (useful fp32-equivalent)" % (name, ms, fl / ms / 1e9))
+    print("%-28s %7.2f ms  %6.1f TFLOP/s (useful fp32-equivalent)" % (name, ms, fl / ms / 1e9))
     return out
-a = timeit("block_project (SIMT)", lambda: ops.block_project(yt, 0, t, d2, starts, bh, bw, w, r))
-b = timeit("block_project_tc", lambda: ops.block_project_tc(yt, 0, t, d2, starts, bh, bw, w, r))
-print("max |tc - simt| / max|simt| = %.2e" % ((a - b).abs().max() / a.abs().max()).item())
-vb = torch.randn((nb, r, t), device=dev)
-c = timeit("block_spatial (SIMT)", lambda: ops.block_spatial(yt, 0, t, d2, starts, bh, bw, vb, rp))
-d = timeit("block_spatial_tc", lambda: ops.block_spatial_tc(yt, 0, t, d2, starts, bh, bw, vb, rp))
-print("max |tc - simt| / max|simt| = %.2e" % ((c - d).abs().max() / c.abs().max()).item())
+if which in ("all", "project"):
+    os.environ["PMD_BLOCK_PROJECT"] = "tc"
+    b = timeit("block_project_tc (smem A)", lambda: ops.block_project_tc(yt, 0, t, d2, starts, bh, bw, w, r))
+    os.environ["PMD_BLOCK_PROJECT"] = "ts"
+    c = timeit("block_project_ts (tmem A)", lambda: ops.block_project_tc(yt, 0, t, d2, starts, bh, bw, w, r))
+    print("max |ts - tc| / max|tc| = %.2e" % ((c - b).abs().max() / b.abs().max()).item())
+if which in ("all", "spatial"):
+    vb = torch.randn((nb, r, t), device=dev)
+    d = timeit("block_spatial_tc", lambda: ops.block_spatial_tc(yt, 0, t, d2, starts, bh, bw, vb, rp))

@@ -121,10 +121,18 @@ struct BTUnit {
     int b, nft;
     int64_t f0;
 };
-__device__ __forceinline__ BTUnit bt_unit(int unit, int n_fg, int64_t ldo) {
+// Unit order: groups of `grp` consecutive blocks (about three rows of the block grid); inside a group the frame group is
+// the slow index and the block the fast one.  The CTAs that run together then work on neighbouring blocks of the SAME
+// frames (the overlapping pixels of neighbouring blocks are served by L2), and a group's coefficient images (~30 MB) stay
+// in L2 across its frame groups.
+__device__ __forceinline__ BTUnit bt_unit(int unit, int n_fg, int64_t ldo, int grp, int nb) {
+    const int per_grp = grp * n_fg;
+    const int g = unit / per_grp, rem = unit - g * per_grp;
+    const int nbg = min(grp, nb - g * grp);                  // blocks of this group (the last one may be smaller)
+    const int fg = rem / nbg;
     BTUnit u;
-    u.b = unit / n_fg;
-    u.f0 = (int64_t)(unit - u.b * n_fg) * (128 * kBTTiles);
+    u.b = g * grp + (rem - fg * nbg);
+    u.f0 = (int64_t)fg * (128 * kBTTiles);
     u.nft = (int)min((int64_t)kBTTiles, (ldo - u.f0 + 127) / 128);
     return u;
 }
@@ -133,7 +141,7 @@ __device__ __forceinline__ BTUnit bt_unit(int unit, int n_fg, int64_t ldo) {
 __global__ void __launch_bounds__(kBTThreads, 1)
 block_project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t rows_per_batch, int d2, const int32_t* __restrict__ starts,
                         int bw, int bpix, int box_h, const unsigned char* __restrict__ bimg, int r, float* __restrict__ out, int64_t ldo,
-                        int n_fg, int n_units) {
+                        int n_fg, int n_units, int grp, int nb) {
     extern __shared__ __align__(1024) unsigned char btsm[];
     __shared__ __align__(8) uint64_t bar_rfull[kBTRawStages], bar_rempty[kBTRawStages], bar_afull[kBTAStages], bar_aempty[kBTAStages],
         bar_bfull[kBTBStages], bar_bempty[kBTBStages], bar_accfull[2], bar_accfree[2];
@@ -185,7 +193,7 @@ block_project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t ro
         const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
         int ucnt = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++ucnt) {
-            const BTUnit u = bt_unit(unit, n_fg, ldo);
+            const BTUnit u = bt_unit(unit, n_fg, ldo, grp, nb);
             const int buf = ucnt & 1;
             bt_mbar_wait(bt_smem_u32(&bar_accfull[buf]), (ucnt >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
@@ -226,7 +234,7 @@ block_project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t ro
         int rs = j;                                                       // raw stage of this group's next item (advances by 2)
         uint32_t ruse = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const BTUnit u = bt_unit(unit, n_fg, ldo);
+            const BTUnit u = bt_unit(unit, n_fg, ldo, grp, nb);
             const int n_items = nch * u.nft;
             const int first = (int)((j - (i_base & 1) + 2) & 1);         // first item of this unit whose global index has parity j
             for (int il = first; il < n_items; il += kBTConvGroups, ++n) {
@@ -277,7 +285,7 @@ block_project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t ro
         int bs = 0, ucnt = 0;                                             // B stage of the next chunk, its use parity
         uint32_t bpar = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++ucnt) {
-            const BTUnit u = bt_unit(unit, n_fg, ldo);
+            const BTUnit u = bt_unit(unit, n_fg, ldo, grp, nb);
             const int buf = ucnt & 1;
             if (ucnt >= 2) {
                 bt_mbar_wait(bt_smem_u32(&bar_accfree[buf]), ((ucnt >> 1) - 1) & 1);
@@ -323,7 +331,7 @@ block_project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t ro
         int rs = 0;
         uint32_t ruse = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-            const BTUnit u = bt_unit(unit, n_fg, ldo);
+            const BTUnit u = bt_unit(unit, n_fg, ldo, grp, nb);
             const int i0 = starts[2 * u.b], j0 = starts[2 * u.b + 1];
             const int64_t row_base = (int64_t)u.b * rows_per_batch;
             for (int kc = 0; kc < nch; ++kc) {
@@ -361,7 +369,7 @@ block_project_ts_kernel(const __grid_constant__ CUtensorMap tm_movie, int64_t ro
             int bs = 0;
             uint32_t buse = 0;
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
-                const BTUnit u = bt_unit(unit, n_fg, ldo);
+                const BTUnit u = bt_unit(unit, n_fg, ldo, grp, nb);
                 const unsigned char* src = bimg + (int64_t)u.b * nch * kBTBStageBytes;
                 for (int kc = 0; kc < nch; ++kc) {
                     if (buse >= 1) bt_mbar_wait(bt_smem_u32(&bar_bempty[bs]), (buse - 1) & 1);
@@ -485,6 +493,6 @@ extern "C" int pmd_block_project_ts(const float* movie_t, int64_t movie_batch_st
     const int grid = (int)(n_units < sms ? n_units : sms);
     pmd::block_project_ts_kernel<<<grid, pmd::kBTThreads, smem, st>>>(tm, movie_batch_stride / ld, (int)d2, starts, (int)bw, bpix, box_h,
                                                                      (const unsigned char*)workspace, (int)r, out, ldo, (int)n_fg,
-                                                                     (int)n_units);
+                                                                     (int)n_units, (int)(nb < sms ? nb : sms), (int)nb);
     return pmd::check_launch(fn);
 }

@@ -175,6 +175,15 @@ int pmd_block_spatial_tc(const float* movie_t, int64_t movie_batch_stride, int64
                          const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* v, int64_t ldv,
                          int64_t r, int64_t rp, float* s, void* stream);
 
+/* the spatial projection with the movie operand in tensor memory (csrc/blocks_ts.cu): every thread streams its pixel's
+ * frames straight into registers, splits them into TF32 hi + bf16 pairs and writes the operand into tensor memory; the
+ * temporal rows are converted once per 32-frame chunk into the shared-memory operand image; accumulators of up to four
+ * 128-pixel tiles stay in tensor memory over the whole frame loop; persistent CTAs.  Same arguments and output as
+ * pmd_block_spatial (any block size; nb unlimited). */
+int pmd_block_spatial_ts(const float* movie_t, int64_t movie_batch_stride, int64_t ld, int64_t d2,
+                         const int32_t* starts, int64_t nb, int64_t bh, int64_t bw, const float* v, int64_t ldv,
+                         int64_t r, int64_t rp, float* s, void* stream);
+
 /* roughness statistics of every component of every block + the keep-through-first-failure rule.
  * replaces: evaluation.py:84-126 (spatial/temporal_roughness_stat), 133-192, 195-222
  *           (filter_by_failures) and decomposition.py:502-506.

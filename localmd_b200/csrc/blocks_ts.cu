@@ -496,3 +496,303 @@ extern "C" int pmd_block_project_ts(const float* movie_t, int64_t movie_batch_st
                                                                      (int)n_units, (int)(nb < sms ? nb : sms), (int)nb);
     return pmd::check_launch(fn);
 }
+
+// =========================================================================================================================
+// Block spatial projection with the movie operand in tensor memory:
+//     s[b][q][c] = sum_f yT[pix(b, q)][f] * v[b][c][f]                              (decomposition.py:304-306)
+// Per (block, 128-pixel tile): D[128 pixels x 64 comps] = A[128 pixels x K frames] * B[K frames x 64 comps].
+//   * A: thread = pixel = tensor-memory lane reads 32 consecutive frames of its own row of the pixel-major movie (one
+//     128-byte line, 8 x ld.global.v4) straight into registers -- one item ahead of the conversion --, splits them into
+//     TF32 hi + bf16 pair and writes the operand into tensor memory (tcgen05.st).  No shared memory on the movie's path.
+//   * B: one warp converts the block's temporal rows (64 comps x 32 frames per chunk) into the K-major SWIZZLE_128B
+//     image (TF32 hi part + bf16 pair part) in shared memory; the chunk is shared by the unit's (up to 4) pixel tiles.
+//   * per 8 frames one kind::tf32 MMA + ONE kind::f16 MMA of K = 16 (as in block_project_ts_kernel); the accumulators of
+//     the 4 tiles (256 columns) stay in tensor memory over the whole frame loop; persistent CTAs walk (block, 512-pixel
+//     group) units.
+// =========================================================================================================================
+namespace pmd {
+
+constexpr int kBSTiles = 4;
+constexpr int kBSBStages = 3;
+constexpr uint32_t kBSAccCols = kBSTiles * kBTN;          // 256
+constexpr int kBSEpiWarps = 4, kBSConvWarps = 8;
+constexpr int kBSMmaWarp = kBSEpiWarps + kBSConvWarps, kBSBWarp = kBSMmaWarp + 1;
+constexpr int kBSThreads = (kBSBWarp + 1) * 32;
+
+__device__ __forceinline__ float4 bs_ldg128(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(kBSThreads, 1)
+block_spatial_ts_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld, int d2, const int32_t* __restrict__ starts, int bw,
+                        int bpix, const float* __restrict__ v, int64_t ldv, int r, int rp, float* __restrict__ s, int n_tg,
+                        int n_units) {
+    extern __shared__ __align__(1024) unsigned char bssm[];
+    __shared__ __align__(8) uint64_t bar_afull[kBTAStages], bar_aempty[kBTAStages], bar_bfull[kBSBStages], bar_bempty[kBSBStages],
+        bar_accfull, bar_accfree;
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t sbase = (bt_smem_u32(bssm) + 1023u) & ~1023u;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nch = (int)((ldv + 31) >> 5);                               // 32-frame chunks
+
+    if (tid == 0) {
+        for (int st = 0; st < kBTAStages; ++st) {
+            bt_mbar_init(bt_smem_u32(&bar_afull[st]), 128);
+            bt_mbar_init(bt_smem_u32(&bar_aempty[st]), 1);
+        }
+        for (int st = 0; st < kBSBStages; ++st) {
+            bt_mbar_init(bt_smem_u32(&bar_bfull[st]), 32);
+            bt_mbar_init(bt_smem_u32(&bar_bempty[st]), 1);
+        }
+        bt_mbar_init(bt_smem_u32(&bar_accfull), 1);
+        bt_mbar_init(bt_smem_u32(&bar_accfree), 32 * kBSEpiWarps);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::);
+    }
+    if (warp == kBSMmaWarp) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(bt_smem_u32(&tmem_base_s)), "r"(512u));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+    const uint32_t tmem = tmem_base_s;
+
+    auto unit_of = [&](int unit, int& b, int& q0, int& nft) {
+        b = unit / n_tg;
+        q0 = (unit - b * n_tg) * (128 * kBSTiles);
+        nft = min(kBSTiles, (bpix - q0 + 127) >> 7);
+    };
+
+    if (warp < kBSEpiWarps) {
+        // ================================ epilogue ================================
+        const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
+        int ucnt = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++ucnt) {
+            int b, q0, nft;
+            unit_of(unit, b, q0, nft);
+            bt_mbar_wait(bt_smem_u32(&bar_accfull), ucnt & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+            for (int ft = 0; ft < nft; ++ft) {
+                const int q = q0 + 128 * ft + 32 * warp + lane;
+#pragma unroll
+                for (int cq = 0; cq < 4; ++cq) {
+                    if (16 * cq < rp) {
+                        uint32_t vv[16];
+                        asm volatile(
+                            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                            : "=r"(vv[0]), "=r"(vv[1]), "=r"(vv[2]), "=r"(vv[3]), "=r"(vv[4]), "=r"(vv[5]), "=r"(vv[6]), "=r"(vv[7]),
+                              "=r"(vv[8]), "=r"(vv[9]), "=r"(vv[10]), "=r"(vv[11]), "=r"(vv[12]), "=r"(vv[13]), "=r"(vv[14]), "=r"(vv[15])
+                            : "r"(lane_base + kBTN * ft + 16 * cq));
+                        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                        if (q < bpix) {
+                            float* o = s + ((int64_t)b * bpix + q) * rp + 16 * cq;
+#pragma unroll
+                            for (int i = 0; i < 16; i += 4) {
+                                if (16 * cq + i < rp)
+                                    *reinterpret_cast<float4*>(o + i) = make_float4(__uint_as_float(vv[i]), __uint_as_float(vv[i + 1]),
+                                                                                    __uint_as_float(vv[i + 2]), __uint_as_float(vv[i + 3]));
+                            }
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+            bt_mbar_arrive(bt_smem_u32(&bar_accfree));
+        }
+    } else if (warp < kBSMmaWarp) {
+        // ================================ converters ================================
+        const int j = (warp - kBSEpiWarps) >> 2;
+        const int m = 32 * (warp & 3) + lane;
+        const uint32_t ta0 = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + kBSAccCols + kBTACols * 2 * j;
+        const uint32_t afull = bt_smem_u32(&bar_afull[2 * j]), aempty = bt_smem_u32(&bar_aempty[2 * j]);
+        int64_t i_base = 0;
+        int n = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            int b, q0, nft;
+            unit_of(unit, b, q0, nft);
+            const int i0 = starts[2 * b], j0 = starts[2 * b + 1];
+            const float* mv = movT + (int64_t)b * mbs;
+            const float* rowp[kBSTiles];                                  // this thread's pixel row in every tile (nullptr: no pixel)
+#pragma unroll
+            for (int ft = 0; ft < kBSTiles; ++ft) {
+                const int q = q0 + 128 * ft + m;
+                const int qi = q / bw, qj = q - qi * bw;
+                rowp[ft] = (ft < nft && q < bpix) ? mv + ((int64_t)(i0 + qi) * d2 + j0 + qj) * ld : nullptr;
+            }
+            const int n_items = nch * nft;
+            const int first = (int)((j - (i_base & 1) + 2) & 1);
+            float4 raw[8];
+            auto load_item = [&](int il) {
+                const int kc = il / nft, ft = il - kc * nft;
+                const float* p = nullptr;
+#pragma unroll
+                for (int t4 = 0; t4 < kBSTiles; ++t4)
+                    if (t4 == ft) p = rowp[t4];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int64_t f = 32 * (int64_t)kc + 4 * c;
+                    raw[c] = (p != nullptr && f < ldv) ? bs_ldg128(p + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            if (first < n_items) load_item(first);
+            for (int il = first; il < n_items; il += kBTConvGroups, ++n) {
+                uint32_t hi[32], pr[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float x[4] = {raw[c].x, raw[c].y, raw[c].z, raw[c].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        hi[4 * c + e] = __float_as_uint(x[e]) & 0xFFFFE000u;
+                        pr[4 * c + e] = bt_pack_bf16(__uint_as_float(hi[4 * c + e]), x[e] - __uint_as_float(hi[4 * c + e]));
+                    }
+                }
+                if (il + kBTConvGroups < n_items) load_item(il + kBTConvGroups);    // next item's line is in flight during the hand-over
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (n >= 1) {
+                        bt_mbar_wait(aempty + 8 * h, (n - 1) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+                    }
+                    uint32_t a[16], p[16];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        a[q] = hi[16 * h + q];
+                        p[q] = pr[16 * h + q];
+                    }
+                    bt_sttm16(ta0 + kBTACols * h, a);
+                    bt_sttm16(ta0 + kBTACols * h + 16, p);
+                    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+                    bt_mbar_arrive(afull + 8 * h);
+                }
+            }
+            i_base += n_items;
+        }
+    } else if (warp == kBSMmaWarp) {
+        // ================================ MMA issuer ================================
+        constexpr uint32_t idesc_tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kBTN >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr uint32_t idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kBTN >> 3) << 17) | ((128u >> 4) << 24);
+        constexpr uint64_t desc_hi = (uint64_t)((1024u >> 4) | (1u << 14) | (2u << 29)) << 32;
+        const bool leader = bt_elect_one();
+        int64_t ig = 0;
+        int bs = 0, ucnt = 0;
+        uint32_t bpar = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++ucnt) {
+            int b, q0, nft;
+            unit_of(unit, b, q0, nft);
+            if (ucnt >= 1) {
+                bt_mbar_wait(bt_smem_u32(&bar_accfree), (ucnt - 1) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+            }
+            for (int kc = 0; kc < nch; ++kc) {
+                bt_mbar_wait(bt_smem_u32(&bar_bfull[bs]), bpar);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+                const uint32_t b_tf = (sbase + bs * kBTBStageBytes) >> 4, b_bf = b_tf + ((kBTN * 128) >> 4);
+                for (int ft = 0; ft < nft; ++ft, ++ig) {
+                    const uint32_t dcol = tmem + kBTN * ft;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int64_t ah = 2 * ig + h;
+                        const int as = (int)(ah & (kBTAStages - 1));
+                        bt_mbar_wait(bt_smem_u32(&bar_afull[as]), (uint32_t)(ah >> 2) & 1);
+                        asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
+                        if (leader) {
+                            const uint32_t a_hi = tmem + kBSAccCols + kBTACols * as, a_pr = a_hi + 16;
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                bt_mma_tf32(dcol, a_hi + 8 * ks, desc_hi | (uint64_t)(b_tf + 2 * (2 * h + ks)), idesc_tf32,
+                                            (uint32_t)((kc | h | ks) != 0));
+                                bt_mma_bf16(dcol, a_pr + 8 * ks, desc_hi | (uint64_t)(b_bf + 2 * (2 * h + ks)), idesc_bf16);
+                            }
+                            bt_commit(bt_smem_u32(&bar_aempty[as]));
+                            if (h == 1 && ft == nft - 1) bt_commit(bt_smem_u32(&bar_bempty[bs]));
+                            if (h == 1 && ft == nft - 1 && kc == nch - 1) bt_commit(bt_smem_u32(&bar_accfull));
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (++bs == kBSBStages) {
+                    bs = 0;
+                    bpar ^= 1;
+                }
+            }
+        }
+    } else {
+        // ================================ temporal rows -> operand image (one warp) ================================
+        // piece id = lane + 32 i (i < 16): 16-byte frame chunk c = id % 8 of component n = id / 8
+        int bs = 0;
+        uint32_t buse = 0;
+        for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            int b, q0, nft;
+            unit_of(unit, b, q0, nft);
+            const float* vb = v + (int64_t)b * r * ldv;
+            for (int kc = 0; kc < nch; ++kc) {
+                float4 x[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int id = lane + 32 * i, c = id & 7, nn = id >> 3;
+                    const int64_t f = 32 * (int64_t)kc + 4 * c;
+                    x[i] = (nn < r && f < ldv) ? bs_ldg128(vb + (int64_t)nn * ldv + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (buse >= 1) bt_mbar_wait(bt_smem_u32(&bar_bempty[bs]), (buse - 1) & 1);
+                const uint32_t base = sbase + bs * kBTBStageBytes;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int id = lane + 32 * i, c = id & 7, nn = id >> 3;
+                    const float xv[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+                    float hi[4];
+                    uint32_t pr[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        hi[e] = __uint_as_float(__float_as_uint(xv[e]) & 0xFFFFE000u);
+                        pr[e] = bt_pack_bf16(xv[e] - hi[e], hi[e]);
+                    }
+                    const uint32_t off = base + (nn >> 3) * 1024 + (nn & 7) * 128 + ((c ^ (nn & 7)) << 4);
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"r"(off), "f"(hi[0]), "f"(hi[1]), "f"(hi[2]), "f"(hi[3]) : "memory");
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(off + kBTN * 128), "r"(pr[0]), "r"(pr[1]), "r"(pr[2]), "r"(pr[3])
+                                 : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+                bt_mbar_arrive(bt_smem_u32(&bar_bfull[bs]));
+                if (++bs == kBSBStages) {
+                    bs = 0;
+                    ++buse;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
+    __syncthreads();
+    if (warp == kBSMmaWarp) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"(512u));
+}
+
+}  // namespace pmd
+
+extern "C" int pmd_block_spatial_ts(const float* movie_t, int64_t movie_batch_stride, int64_t ld, int64_t d2, const int32_t* starts,
+                                    int64_t nb, int64_t bh, int64_t bw, const float* v, int64_t ldv, int64_t r, int64_t rp, float* s,
+                                    void* stream) {
+    const char* fn = "pmd_block_spatial_ts";
+    PMD_REQUIRE(movie_t && starts && v && s, fn, "null pointer");
+    PMD_REQUIRE(ld > 0 && ld % 4 == 0 && ldv > 0 && ldv % 4 == 0 && ldv <= ld && nb > 0 && r > 0 && rp >= r && rp % 4 == 0 && rp <= 64, fn,
+                "bad size (ld, ldv multiples of 4, ldv <= ld, rp multiple of 4, r <= rp <= 64)");
+    PMD_REQUIRE(((uintptr_t)movie_t % 16) == 0 && ((uintptr_t)v % 16) == 0 && ((uintptr_t)s % 16) == 0 && (movie_batch_stride % 4) == 0,
+                fn, "operands must be 16-byte aligned");
+    const int64_t bpix = bh * bw;
+    const int64_t n_tg = (bpix + 128 * pmd::kBSTiles - 1) / (128 * pmd::kBSTiles), n_units = nb * n_tg;
+    PMD_REQUIRE(n_units < (1ll << 31) && bpix < (1ll << 30), fn, "too many (block, pixel group) units");
+    const int smem = pmd::kBSBStages * pmd::kBTBStageBytes + 1024;
+    cudaError_t e = cudaFuncSetAttribute(pmd::block_spatial_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+        pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e));
+        return (int)e;
+    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = (int)(n_units < sms ? n_units : sms);
+    pmd::block_spatial_ts_kernel<<<grid, pmd::kBSThreads, smem, (cudaStream_t)stream>>>(
+        movie_t, movie_batch_stride, ld, (int)d2, starts, (int)bw, (int)bpix, v, ldv, (int)r, (int)rp, s, (int)n_tg, (int)n_units);
+    return pmd::check_launch(fn);
+}

@@ -377,6 +377,10 @@ def block_spatial_tc(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, v, rp)
     _req(movie_t, torch.float32, "movie_t"), _req(v, torch.float32, "v"), _req(starts, torch.int32, "starts")
     nb, r, ldv = v.shape
     s_out = torch.empty((nb, bh * bw, rp), dtype=torch.float32, device=movie_t.device)
+    if os.environ.get("PMD_BLOCK_SPATIAL", "ts") == "ts":   # development switch between the generations of the kernel
+        _call("pmd_block_spatial_ts", _p(movie_t), movie_batch_stride, ld, d2, _p(starts), nb, bh, bw, _p(v.contiguous()), ldv, r, rp,
+              _p(s_out), _stream())
+        return s_out
     step = 65535
     for s in range(0, nb, step):
         m = min(step, nb - s)

@@ -33,4 +33,8 @@ if which in ("all", "project"):
     print("max |ts - tc| / max|tc| = %.2e" % ((c - b).abs().max() / b.abs().max()).item())
 if which in ("all", "spatial"):
     vb = torch.randn((nb, r, t), device=dev)
-    d = timeit("block_spatial_tc", lambda: ops.block_spatial_tc(yt, 0, t, d2, starts, bh, bw, vb, rp))
+    os.environ["PMD_BLOCK_SPATIAL"] = "tc"
+    d = timeit("block_spatial_tc (smem A)", lambda: ops.block_spatial_tc(yt, 0, t, d2, starts, bh, bw, vb, rp))
+    os.environ["PMD_BLOCK_SPATIAL"] = "ts"
+    e = timeit("block_spatial_ts (tmem A)", lambda: ops.block_spatial_tc(yt, 0, t, d2, starts, bh, bw, vb, rp))
+    print("max |ts - tc| / max|tc| = %.2e" % ((e - d).abs().max() / d.abs().max()).item())

@@ -513,15 +513,15 @@ extern "C" int pmd_block_project_ts(const float* movie_t, int64_t movie_batch_st
 namespace pmd {
 
 constexpr int kBSTiles = 4;
-constexpr int kBSBStages = 3;
+constexpr int kBSBStages = 6, kBSAStages = 8;
 constexpr uint32_t kBSAccCols = kBSTiles * kBTN;          // 256
 constexpr int kBSEpiWarps = 4, kBSConvWarps = 8;
-constexpr int kBSMmaWarp = kBSEpiWarps + kBSConvWarps, kBSBWarp = kBSMmaWarp + 1;
-constexpr int kBSThreads = (kBSBWarp + 1) * 32;
+constexpr int kBSMmaWarp = kBSEpiWarps + kBSConvWarps, kBSBWarp = kBSMmaWarp + 1, kBSBWarps = 2;
+constexpr int kBSThreads = (kBSBWarp + kBSBWarps) * 32;
 
 __device__ __forceinline__ float4 bs_ldg128(const float* p) {
     float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
     return v;
 }
 
@@ -530,7 +530,7 @@ block_spatial_ts_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld,
                         int bpix, const float* __restrict__ v, int64_t ldv, int r, int rp, float* __restrict__ s, int n_tg,
                         int n_units) {
     extern __shared__ __align__(1024) unsigned char bssm[];
-    __shared__ __align__(8) uint64_t bar_afull[kBTAStages], bar_aempty[kBTAStages], bar_bfull[kBSBStages], bar_bempty[kBSBStages],
+    __shared__ __align__(8) uint64_t bar_afull[kBSAStages], bar_aempty[kBSAStages], bar_bfull[kBSBStages], bar_bempty[kBSBStages],
         bar_accfull, bar_accfree;
     __shared__ uint32_t tmem_base_s;
     const uint32_t sbase = (bt_smem_u32(bssm) + 1023u) & ~1023u;
@@ -538,7 +538,7 @@ block_spatial_ts_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld,
     const int nch = (int)((ldv + 31) >> 5);                               // 32-frame chunks
 
     if (tid == 0) {
-        for (int st = 0; st < kBTAStages; ++st) {
+        for (int st = 0; st < kBSAStages; ++st) {
             bt_mbar_init(bt_smem_u32(&bar_afull[st]), 128);
             bt_mbar_init(bt_smem_u32(&bar_aempty[st]), 1);
         }
@@ -605,8 +605,10 @@ block_spatial_ts_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld,
         // ================================ converters ================================
         const int j = (warp - kBSEpiWarps) >> 2;
         const int m = 32 * (warp & 3) + lane;
-        const uint32_t ta0 = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + kBSAccCols + kBTACols * 2 * j;
-        const uint32_t afull = bt_smem_u32(&bar_afull[2 * j]), aempty = bt_smem_u32(&bar_aempty[2 * j]);
+        // A half-stages (16 frames each): item n of group j uses 4 (n & 1) + 2 j + h -- two items of buffering per group, so a
+        // group converts one item ahead of the MMAs of its previous one (with one item per group the hand-over latency of
+        // store -> MMA -> commit bounded the whole kernel)
+        const uint32_t ta_lane = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + kBSAccCols;
         int64_t i_base = 0;
         int n = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
@@ -649,10 +651,19 @@ block_spatial_ts_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld,
                     }
                 }
                 if (il + kBTConvGroups < n_items) load_item(il + kBTConvGroups);    // next item's line is in flight during the hand-over
+                if (il + 3 * kBTConvGroups < n_items) {                              // and the line after the next two is asked into L2
+                    const int il2 = il + 3 * kBTConvGroups, kc2 = il2 / nft, ft2 = il2 - kc2 * nft;
+                    const float* p2 = nullptr;
+#pragma unroll
+                    for (int t4 = 0; t4 < kBSTiles; ++t4)
+                        if (t4 == ft2) p2 = rowp[t4];
+                    if (p2 != nullptr && 32 * (int64_t)kc2 < ldv) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p2 + 32 * (int64_t)kc2));
+                }
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
-                    if (n >= 1) {
-                        bt_mbar_wait(aempty + 8 * h, (n - 1) & 1);
+                    const int as = 4 * (n & 1) + 2 * j + h;
+                    if (n >= 2) {
+                        bt_mbar_wait(bt_smem_u32(&bar_aempty[as]), ((n >> 1) - 1) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
                     }
                     uint32_t a[16], p[16];
@@ -661,11 +672,11 @@ block_spatial_ts_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld,
                         a[q] = hi[16 * h + q];
                         p[q] = pr[16 * h + q];
                     }
-                    bt_sttm16(ta0 + kBTACols * h, a);
-                    bt_sttm16(ta0 + kBTACols * h + 16, p);
+                    bt_sttm16(ta_lane + kBTACols * as, a);
+                    bt_sttm16(ta_lane + kBTACols * as + 16, p);
                     asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;\n" ::);
-                    bt_mbar_arrive(afull + 8 * h);
+                    bt_mbar_arrive(bt_smem_u32(&bar_afull[as]));
                 }
             }
             i_base += n_items;
@@ -694,9 +705,8 @@ block_spatial_ts_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld,
                     const uint32_t dcol = tmem + kBTN * ft;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int64_t ah = 2 * ig + h;
-                        const int as = (int)(ah & (kBTAStages - 1));
-                        bt_mbar_wait(bt_smem_u32(&bar_afull[as]), (uint32_t)(ah >> 2) & 1);
+                        const int as = 4 * (int)((ig >> 1) & 1) + 2 * (int)(ig & 1) + h;   // item ig = item ig >> 1 of group ig & 1
+                        bt_mbar_wait(bt_smem_u32(&bar_afull[as]), (uint32_t)(ig >> 2) & 1);
                         asm volatile("tcgen05.fence::after_thread_sync;\n" ::);
                         if (leader) {
                             const uint32_t a_hi = tmem + kBSAccCols + kBTACols * as, a_pr = a_hi + 16;
@@ -720,22 +730,32 @@ block_spatial_ts_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld,
             }
         }
     } else {
-        // ================================ temporal rows -> operand image (one warp) ================================
-        // piece id = lane + 32 i (i < 16): 16-byte frame chunk c = id % 8 of component n = id / 8
-        int bs = 0;
-        uint32_t buse = 0;
+        // ================================ temporal rows -> operand image (two warps, alternate chunks) ================================
+        // piece id = lane + 32 i (i < 16): 16-byte frame chunk c = id % 8 of component n = id / 8.  A warp's next chunk is
+        // requested as soon as the current one is converted, so its global-memory latency overlaps the MMAs of the chunk
+        // the other warp delivers.
+        const int wb = warp - kBSBWarp;
+        int64_t gb_base = 0;                                              // chunks before this unit
+        float4 x[16];
+        const float* vb = nullptr;
+        auto load_chunk = [&](int kc) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const int id = lane + 32 * i, c = id & 7, nn = id >> 3;
+                const int64_t f = 32 * (int64_t)kc + 4 * c;
+                x[i] = (nn < r && f < ldv) ? bs_ldg128(vb + (int64_t)nn * ldv + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        };
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             int b, q0, nft;
             unit_of(unit, b, q0, nft);
-            const float* vb = v + (int64_t)b * r * ldv;
-            for (int kc = 0; kc < nch; ++kc) {
-                float4 x[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int id = lane + 32 * i, c = id & 7, nn = id >> 3;
-                    const int64_t f = 32 * (int64_t)kc + 4 * c;
-                    x[i] = (nn < r && f < ldv) ? bs_ldg128(vb + (int64_t)nn * ldv + f) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+            vb = v + (int64_t)b * r * ldv;
+            const int first = (int)((wb - (gb_base & 1) + 2) & 1);        // first chunk of this unit whose global index has parity wb
+            if (first < nch) load_chunk(first);
+            for (int kc = first; kc < nch; kc += kBSBWarps) {
+                const int64_t gb = gb_base + kc;
+                const int bs = (int)(gb % kBSBStages);
+                const uint32_t buse = (uint32_t)(gb / kBSBStages);
                 if (buse >= 1) bt_mbar_wait(bt_smem_u32(&bar_bempty[bs]), (buse - 1) & 1);
                 const uint32_t base = sbase + bs * kBTBStageBytes;
 #pragma unroll
@@ -756,11 +776,9 @@ block_spatial_ts_kernel(const float* __restrict__ movT, int64_t mbs, int64_t ld,
                 }
                 asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy writes -> visible to the tensor core
                 bt_mbar_arrive(bt_smem_u32(&bar_bfull[bs]));
-                if (++bs == kBSBStages) {
-                    bs = 0;
-                    ++buse;
-                }
+                if (kc + kBSBWarps < nch) load_chunk(kc + kBSBWarps);
             }
+            gb_base += nch;
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::);

@@ -1006,33 +1006,68 @@ def localmd_decomposition(
             raise ValueError("max_components > 102 is not supported by the sm_100a Jacobi kernel")
         if r > 64:
             raise ValueError("max_components > 64 is not supported by the sm_100a block kernels")
+        dim_1_iters, dim_2_iters = tile_starts(d1, bh), tile_starts(d2, bw)
+        starts = np.stack(np.meshgrid(dim_1_iters, dim_2_iters, indexing="ij"), axis=-1).reshape(-1, 2).astype(np.int32)
+        nb = starts.shape[0]
+        # blocks are partitioned over the ranks (contiguous index ranges); results are all-gathered below
+        b0, b1 = sharding.block_partition(nb, world)[rank]
+        row_lo, row_hi = 0, d1                                   # image rows of the init movie this rank holds
         if group is None:
             src2d, idx = movie.frame_source(frames[:crop])
-        else:  # the init window lives on its owner rank(s): every rank receives the raw frames
-            src2d = sharding.gather_frames(movie, frames[:crop], group, bounds)
+            yt = ops.standardize_frames_t(src2d, idx, mean, std)  # (d, ld)
+            del src2d, idx
+            own_lo, own_hi = 0, d1
+        else:
+            # Patch-partitioned init window: this rank receives from the window's owner rank(s) only the
+            # image rows its blocks cover and standardises those; sums over the field of view (the background traces) are
+            # taken over a disjoint row cover and all-reduced.
+            parts = sharding.block_partition(nb, world)
+            ranges = sharding.block_row_ranges(starts, bh, parts)
+            if any(hi_ <= lo_ for lo_, hi_ in ranges):            # more ranks than blocks: every rank takes the whole window
+                ranges = [(0, d1)] * world
+                owned = [(0, d1) if r_ == 0 else (0, 0) for r_ in range(world)]
+            else:
+                owned = sharding.owned_row_ranges(ranges, d1)
+            row_lo, row_hi = ranges[rank]
+            own_lo, own_hi = owned[rank]
+            src2d = sharding.exchange_frame_rows(movie, frames[:crop], ranges, d2, group, bounds)
             idx = torch.arange(src2d.shape[0], dtype=torch.int64, device=dev)
-        yt = ops.standardize_frames_t(src2d, idx, mean, std)  # (d, ld)
-        del src2d, idx
-        if bg.shape[0] <= 16:   # skinny contractions: one streaming pass over yt each (csrc/bgfilter.cu)
+            yt = ops.standardize_frames_t(src2d, idx, mean[row_lo * d2 : row_hi * d2].contiguous(),
+                                          std[row_lo * d2 : row_hi * d2].contiguous())  # (local pixels, ld)
+            del src2d, idx
+        bg_loc = bg[:, row_lo * d2 : row_hi * d2].contiguous() if (row_lo, row_hi) != (0, d1) else bg
+        if group is not None:
+            import torch.distributed as dist
+
+            o0, o1 = (own_lo - row_lo) * d2, (own_hi - row_lo) * d2
+            if o1 > o0:
+                bo = bg_loc[:, o0:o1].contiguous()
+                vbg = ops.bg_project_t(yt[o0:o1], bo) if bo.shape[0] <= 16 else torch.matmul(bo, yt[o0:o1]).contiguous()
+            else:
+                vbg = torch.zeros((bg.shape[0], yt.shape[1]), dtype=torch.float32, device=dev)
+            dist.all_reduce(vbg, group=group)
+            if bg.shape[0] <= 16:
+                ops.bg_remove_t(yt, bg_loc, vbg)
+            else:
+                yt.addmm_(bg_loc.t(), vbg, alpha=-1.0)
+        elif bg.shape[0] <= 16:   # skinny contractions: one streaming pass over yt each (csrc/bgfilter.cu)
             vbg = ops.bg_project_t(yt, bg)  # (K, ld)
             ops.bg_remove_t(yt, bg, vbg)
         else:
             vbg = torch.matmul(bg, yt).contiguous()  # (K, ld)
             yt.addmm_(bg.t(), vbg, alpha=-1.0)
         if pixel_weighting is not None:
-            yt *= _as_dev(np.asarray(pixel_weighting, dtype=np.float32).reshape(-1), dev)[:, None]
+            pw = _as_dev(np.asarray(pixel_weighting, dtype=np.float32).reshape(-1), dev)
+            yt *= pw[row_lo * d2 : row_hi * d2][:, None]
         tm.mark("init_filter")
 
-        dim_1_iters, dim_2_iters = tile_starts(d1, bh), tile_starts(d2, bw)
-        starts = np.stack(np.meshgrid(dim_1_iters, dim_2_iters, indexing="ij"), axis=-1).reshape(-1, 2).astype(np.int32)
-        nb = starts.shape[0]
         starts_dev = torch.from_numpy(starts).to(dev)
+        # block origins relative to the rows of the init movie this rank holds
+        starts_fit = starts_dev if row_lo == 0 else (starts_dev - torch.tensor([row_lo, 0], dtype=torch.int32, device=dev))
         block_weights = pyramid_weights(bh, bw)
 
         # ---- block fits (decomposition.py:790-838) -------------------------------------------------
         bs = take("block_sketches")
-        # blocks are partitioned over the ranks (contiguous index ranges); results are all-gathered below
-        b0, b1 = sharding.block_partition(nb, world)[rank]
         windowed = window_chunks < crop
         if not windowed:
             if bs is not None:
@@ -1040,7 +1075,7 @@ def localmd_decomposition(
             else:
                 sketches = torch.randn((nb, crop // temporal_avg_factor, r + 10), generator=gen, device=dev, dtype=torch.float32)
             u_blk, v_blk, ranks_loc, sstat, tstat = block_decompositions(
-                yt, crop, d2, starts_dev[b0:b1], bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
+                yt, crop, d2, starts_fit[b0:b1].contiguous(), bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
                 int(max_consecutive_failures), sketches[b0:b1], spatial_denoiser, temporal_denoiser,
             )
         else:
@@ -1055,7 +1090,7 @@ def localmd_decomposition(
                 sketches = [torch.randn((nb, window_chunks // temporal_avg_factor, r + 10), generator=gen, device=dev,
                                         dtype=torch.float32)[b0:b1] for _ in range(n_win)]
             u_blk, v_blk, ranks_loc, sstat, tstat = block_decompositions_windowed(
-                yt, crop, d2, starts_dev[b0:b1].contiguous(), bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
+                yt, crop, d2, starts_fit[b0:b1].contiguous(), bh, bw, r, temporal_avg_factor, spatial_avg_factor, thr_s, thr_t,
                 int(max_consecutive_failures), sketches, int(window_chunks), spatial_denoiser, temporal_denoiser,
             )
         del sketches

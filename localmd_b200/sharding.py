@@ -5,8 +5,11 @@ cut into contiguous frame ranges aligned to the 1024-frame chunks of the stats p
 two full-movie passes (mean/noise, projection) need no data-path communication at all.  What is exchanged:
 
   * all-reduce of the per-pixel mean / noise partial sums (2 x d floats) after the stats pass,
-  * the init window and the background sample: raw frames held by their owner ranks -> every rank
-    (ragged all-gather by per-rank broadcasts, moved as bytes so every movie dtype works),
+  * the background sample: raw frames held by their owner ranks -> every rank (ragged all-gather by per-rank broadcasts,
+    moved as bytes so every movie dtype works),
+  * the init window, PATCH PARTITIONED: a rank fits a contiguous range of blocks and receives from the window's owner
+    rank(s) only the image rows those blocks cover (its rows plus half a block of halo) -- point-to-point sends of one
+    slab per (owner, receiver) pair instead of N broadcasts of the whole window,
   * the per-block results (kept spatial components + their temporal traces): blocks are partitioned over the
     ranks, results all-gathered (ragged) so that every rank holds the same sparse U,
   * all-reduce of the k x k Gram of the projected movie before the final eigendecomposition,
@@ -111,3 +114,89 @@ def all_reduce_sum(t: torch.Tensor, group) -> torch.Tensor:
 
         dist.all_reduce(t, group=group)
     return t
+
+
+def block_row_ranges(starts, bh: int, parts: Sequence[Tuple[int, int]]) -> List[Tuple[int, int]]:
+    """Image-row range [r_lo, r_hi) covered by the blocks starts[b0:b1] of every rank (blocks in row-major order of their
+    starts, as the reference enumerates them); (0, 0) for a rank without blocks."""
+    out = []
+    for b0, b1 in parts:
+        if b1 <= b0:
+            out.append((0, 0))
+        else:
+            out.append((int(starts[b0][0]), int(starts[b1 - 1][0]) + int(bh)))
+    return out
+
+
+def owned_row_ranges(ranges: Sequence[Tuple[int, int]], d1: int) -> List[Tuple[int, int]]:
+    """A disjoint cover of the image rows [0, d1) by the ranks: rank k owns the rows from the start of its range up to
+    the start of the next non-empty rank's range (sums over the field of view, e.g. the background traces, count every
+    pixel exactly once)."""
+    los = [lo for lo, hi in ranges if hi > lo]
+    out, k = [], 0
+    for lo, hi in ranges:
+        if hi <= lo:
+            out.append((0, 0))
+            continue
+        nxt = los[k + 1] if k + 1 < len(los) else d1
+        out.append((0 if k == 0 else lo, max(nxt, lo) if k + 1 < len(los) else d1))
+        k += 1
+    return out
+
+
+def exchange_frame_rows(movie, frame_ids: Sequence[int], row_ranges: Sequence[Tuple[int, int]], d2: int, group,
+                        bounds: Optional[Sequence[Tuple[int, int]]] = None) -> torch.Tensor:
+    """Patch-partitioned gather: rank k gets, for ALL requested global frames (in the requested order), the pixels of the
+    image rows row_ranges[k] = [r_lo, r_hi) -> (n_frames, (r_hi - r_lo) * d2) in the movie's dtype.  Every owner rank
+    reads the requested frames of its shard once and sends one contiguous slab to every receiver (point to point)."""
+    import torch.distributed as dist
+
+    ids = [int(f) for f in frame_ids]
+    rank, world = dist_info(group)
+    bounds = bounds if bounds is not None else shard_bounds(movie.T_total, world)
+    own = owners_of(ids, bounds)
+    order = sorted(range(len(ids)), key=lambda i: (own[i], i))
+    counts = [sum(1 for o in own if o == r) for r in range(world)]
+    mine = [ids[i] for i in order if own[i] == rank]
+    lo, hi = row_ranges[rank]
+    n_pix = (hi - lo) * d2
+    out = torch.empty((len(ids), n_pix), dtype=movie.torch_dtype, device=movie.device)
+    as_bytes = movie.torch_dtype not in (torch.float32, torch.float64, torch.int32, torch.int64)
+    view = (lambda t: t.view(torch.uint8)) if as_bytes else (lambda t: t)
+    ops, keep = [], []
+    local = None                                                     # (my frames, d)
+    if mine:
+        src = None
+        if mine == list(range(mine[0], mine[0] + len(mine))) and hasattr(movie, "frame_source"):
+            src, idx = movie.frame_source(mine)                      # resident shard: a view, no copy of the frames
+            i0 = int(idx[0].item()) if idx.numel() else 0
+            local = src[i0 : i0 + len(mine)] if src.shape[0] >= i0 + len(mine) and bool((idx == torch.arange(
+                i0, i0 + len(mine), device=idx.device)).all()) else None
+        if local is None:
+            local = movie.gather(mine)
+    offs = [sum(counts[:r]) for r in range(world)]
+    for k in range(world):                                           # my frames -> every receiver's rows
+        klo, khi = row_ranges[k]
+        if local is None or khi <= klo:
+            continue
+        slab = local[:, klo * d2 : khi * d2]
+        if k == rank:
+            out[offs[rank] : offs[rank] + counts[rank]].copy_(slab)
+        else:
+            slab = slab.contiguous()
+            keep.append(slab)
+            ops.append(dist.P2POp(dist.isend, view(slab), dist.get_global_rank(group, k) if group is not None else k, group))
+    if n_pix > 0:
+        for o in range(world):                                       # every owner's frames of my rows
+            if o != rank and counts[o]:
+                seg = out[offs[o] : offs[o] + counts[o]]
+                ops.append(dist.P2POp(dist.irecv, view(seg), dist.get_global_rank(group, o) if group is not None else o, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    if len(ids) and order != list(range(len(ids))):                  # rows are grouped by owner: restore the requested order
+        inv = torch.empty(len(ids), dtype=torch.int64)
+        inv[torch.tensor(order, dtype=torch.int64)] = torch.arange(len(ids), dtype=torch.int64)
+        inv = inv.to(out.device)
+        out = out.index_select(0, inv) if out.dtype != torch.uint16 else out.view(torch.int16).index_select(0, inv).view(torch.uint16)
+    return out

@@ -98,6 +98,31 @@ def test_gather_frames_gloo():
     _run(_gather)
 
 
+def _exchange(rank, world):
+    T, d1, d2 = 5000, 12, 5
+    g = torch.Generator().manual_seed(1)
+    starts = [(r, c) for r in (0, 2, 4, 6, 8) for c in (0, 1)]       # 10 blocks of height 4, row-major
+    parts = sharding.block_partition(len(starts), world)
+    ranges = sharding.block_row_ranges(starts, 4, parts)
+    assert ranges[0][0] == 0 and ranges[-1][1] == d1 and all(ranges[i][1] >= ranges[i + 1][0] for i in range(world - 1))
+    owned = sharding.owned_row_ranges(ranges, d1)
+    assert owned[0][0] == 0 and owned[-1][1] == d1 and all(owned[i][1] == owned[i + 1][0] for i in range(world - 1))
+    for dtype in (torch.float32, torch.uint16):
+        full = (torch.rand((T, d1 * d2), generator=g) * 1000).to(dtype)
+        bounds = sharding.shard_bounds(T, world)
+        movie = _FakeMovie(full, *bounds[rank])
+        for ids in (list(range(2000, 2600)), [4999, 0, 1023, 1024, 3000, 17], list(range(100, 140))):
+            got = sharding.exchange_frame_rows(movie, ids, ranges, d2, dist.group.WORLD, bounds)
+            lo, hi = ranges[rank]
+            want = full[torch.tensor(ids)][:, lo * d2 : hi * d2]
+            assert got.shape == want.shape and torch.equal(got.to(torch.float64), want.to(torch.float64))
+
+
+def test_exchange_frame_rows_gloo():
+    _run(_exchange)
+    _run(_exchange, 3)
+
+
 def _svd(rank, world):
     from localmd_b200.decomposition import projected_svd
 

@@ -784,10 +784,11 @@ def sparse_u_from_scipy(u, device=None):
     )
 
 
-def projected_svd(projection, data, group=None):
+def projected_svd(projection, data, group=None, after_gram=None):
     """decomposition.py:1013-1137: Gram-based SVD of `data` (k, n) and R = projection @ left.
     With `group`, `data` holds this rank's frame columns: the k x k Gram is all-reduced and the
-    returned Vt is the local column block."""
+    returned Vt is the local column block.  after_gram: optional callable invoked once the Gram has been enqueued (the
+    driver starts side-stream work there that should overlap the latency-bound eigensolver, not the GEMM)."""
     dev = data.device
     projection = _as_dev(projection, dev)
     k, n = data.shape
@@ -806,6 +807,8 @@ def projected_svd(projection, data, group=None):
             dist.all_reduce(gram, group=group)
         gram = 0.5 * (gram + gram.t())
         _submark("final_svd.gram")
+        if after_gram is not None:
+            after_gram()
         vals, left = sym_eigh_desc_abs(gram)
         _submark("final_svd.eigh")
         sing = torch.sqrt(vals).to(torch.float32)
@@ -1153,7 +1156,8 @@ def localmd_decomposition(
                     raise ValueError("prune_sketch has shape %s, expected %s" % (tuple(ps.shape), shape))
             else:
                 ps = torch.randn(shape, generator=gen, device=dev, dtype=torch.float32)
-            p = compute_lowrank_factorized_svd(su, torch.matmul(v_init, ps), only_left=True, factor="chol")
+            # the prune sketch V Omega (R x t)(t x k'): float32-accurate on the tensor cores (3xTF32) instead of a SIMT GEMM
+            p = compute_lowrank_factorized_svd(su, ops.matmul_3xtf32_any(v_init, ps), only_left=True, factor="chol")
         else:
             p = compute_lowrank_factorized_svd(su, v_init, only_left=True, factor="chol")
         say("After performing rank reduction, the updated rank is {}".format(p.shape[1]))
@@ -1168,16 +1172,23 @@ def localmd_decomposition(
         # beside the final SVD, whose float64 eigensolver leaves most of the GPU idle.
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev)
-        side.wait_stream(main)
         row_ids = torch.from_numpy(np.arange(d).reshape((d1, d2), order=order).reshape(-1)).to(dev)
-        with torch.cuda.stream(side):
-            indptr, indices, values = su.csr(row_ids)
-            csr32 = su.csr_physical32()
-        for t_ in (indptr, indices, values) + tuple(csr32):
-            t_.record_stream(main)
+        csr_out = {}
+
+        def start_csr():
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                csr_out["csr"] = su.csr(row_ids)
+                csr_out["csr32"] = su.csr_physical32()
 
         # ---- final SVD (decomposition.py:896-904) ---------------------------------------------------
-        rmix, s, vt = projected_svd(p, v_full, group)
+        rmix, s, vt = projected_svd(p, v_full, group, after_gram=start_csr)
+        if not csr_out:          # k > T path of projected_svd: no Gram hook
+            start_csr()
+        indptr, indices, values = csr_out["csr"]
+        csr32 = csr_out["csr32"]
+        for t_ in (indptr, indices, values) + tuple(csr32):
+            t_.record_stream(main)
         good = s != 0
         rmix, s, vt = rmix[:, good], s[good], vt[good, :]
         if group is not None:  # Vt column shards -> the full (k, T) factor on every rank

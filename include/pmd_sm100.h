@@ -108,12 +108,31 @@ int pmd_block_orth(float* x, int64_t batch, int64_t m, int64_t n, int64_t ldx, c
  *   pmd_bg_project_t: part[g][c][f] = sum over the pixels of range g of bg[c][p] * yt[p][f]   (n_ranges equal pixel
  *                     ranges; the caller sums the partials over g in a fixed order -> vbg [k][ld], deterministic)
  *   pmd_bg_remove_t:  yt[p][f] -= sum_c bg[c][p] * vbg[c][f]
- * bg: [k][d] float32 orthonormal background rows, 1 <= k <= 16.
+ * bg: [k][d] float32 orthonormal background rows, 1 <= k <= 16 (pmd_bg_project_t alone also takes 17 <= k <= 32: the
+ *     sketch coefficients of the background rSVD below).
  * replaces: pmd_loader.py:386-387 (standardize_and_filter: temporal projection onto the spatial background basis
  *           and its subtraction) on the init frames. */
 int pmd_bg_project_t(const float* yt, int64_t ld, int64_t d, const float* bg, int64_t k, int64_t n_ranges, float* part,
                      void* stream);
 int pmd_bg_remove_t(float* yt, int64_t ld, int64_t d, const float* bg, int64_t k, const float* vbg, void* stream);
+
+/* Background basis: the two skinny contractions of the randomised SVD of the sampled standardised frames
+ * (pmd_loader.py:46-68, called from 300-314) on their pixel-major copy yt [d][ld] (pmd_standardize_frames_t):
+ *   pmd_rows_sketch:       y[p][j] = sum_{f < n} yt[p][f] * omega[f][j]        omega [n][l] row-major, 1 <= l <= 32
+ *                          (the coefficient pass  q^T yt  is pmd_bg_project_t with k = l)
+ *   pmd_rows_times_small:  out[b][p][c] = sum_{j < k} x[b][p][j] * m[b][j][c]   k, nc <= 32; transposed != 0 writes
+ *                          out[b][c][p] instead (row pitch ldo either way).  Used for the orthonormalisation passes
+ *                          (x @ whitening transform) and the rotation into singular vectors.  Not in place.
+ *   pmd_chol_whiten:       t[b] = L^-T (float32, n x n) of the Cholesky factor g[b] = L L^T of a float64 Gram matrix,
+ *                          n <= 32: x @ t is an orthonormal basis of the range of x when g = x^T x (CholQR; two rounds
+ *                          replace the QR of pmd_loader.py:59).  Numerically dependent columns give zero columns.
+ * replaces: the jnp.matmul / jnp.linalg.qr / svd chain of pmd_loader.py:55-68 (random_svd of the background frames). */
+int pmd_chol_whiten(const double* g, int64_t batch, int64_t n, float* t, void* stream);
+int pmd_rows_sketch(const float* yt, int64_t ld, int64_t d, int64_t n, const float* omega, int64_t l, float* y, int64_t ldy,
+                    void* stream);
+int pmd_rows_times_small(const float* x, int64_t ldx, int64_t d, int64_t k, const float* m, int64_t ldm, int64_t nc, float* out,
+                         int64_t ldo, int transposed, int64_t batch, int64_t batch_stride_x, int64_t batch_stride_m,
+                         int64_t batch_stride_o, void* stream);
 
 /* 2x2(-ish) average pooling + temporal averaging of every block of the standardised init movie.
  * replaces: decomposition.py:192-232 (downsample_average_pooling) + 283-290.

@@ -15,20 +15,38 @@ constexpr int kBGThreads = 256;
 constexpr int kBGPix = 256;   // pixels staged per shared-memory refill
 constexpr int kBGBatch = 4;   // pixel rows per pipeline step of the projection (two steps in flight per thread)
 
-// part[g][k][f] = sum over the pixels of range g
+// packed float32 pairs (Blackwell FFMA2): one instruction per two multiply-adds of the inner loops, which are bound by
+// instruction issue at the 8 warps per SM their accumulator count allows
+__device__ __forceinline__ uint64_t bg_pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};\n" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void bg_unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;\n" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t bg_fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;\n" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// part[g][k][f] = sum over the pixels of range g   (KM = 16: background removal; KM = 32: the sketch coefficients of the
+// background rSVD, csrc/bgbasis.cu)
+template <int KM>
 __global__ void __launch_bounds__(kBGThreads)
 bg_project_t_kernel(const float* __restrict__ yt, int64_t ld, int64_t d, const float* __restrict__ bg, int k_n, int64_t pix_per_cta,
                     float* __restrict__ part) {
-    __shared__ float sb[kBGK][kBGPix];
+    __shared__ float sb[KM][kBGPix];
     const int64_t f = ((int64_t)blockIdx.x * kBGThreads + threadIdx.x) * 4;
     const int64_t p0 = (int64_t)blockIdx.y * pix_per_cta, p1 = min(d, p0 + pix_per_cta);
-    float4 acc[kBGK];
+    uint64_t acc[KM][2];   // (frames f, f + 1) and (f + 2, f + 3) of component k
 #pragma unroll
-    for (int k = 0; k < kBGK; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < KM; ++k) acc[k][0] = acc[k][1] = 0ull;
     for (int64_t pb = p0; pb < p1; pb += kBGPix) {
         const int n = (int)min((int64_t)kBGPix, p1 - pb);
         __syncthreads();
-        for (int i = threadIdx.x; i < kBGK * kBGPix; i += kBGThreads) {
+        for (int i = threadIdx.x; i < KM * kBGPix; i += kBGThreads) {
             const int k = i / kBGPix, q = i - k * kBGPix;
             sb[k][q] = (k < k_n && q < n) ? bg[(int64_t)k * d + pb + q] : 0.f;
         }
@@ -47,13 +65,13 @@ bg_project_t_kernel(const float* __restrict__ yt, int64_t ld, int64_t d, const f
                 load(nxt, q0 + kBGBatch);
 #pragma unroll
                 for (int j = 0; j < kBGBatch; ++j) {
+                    const uint64_t y01 = bg_pack2(cur[j].x, cur[j].y), y23 = bg_pack2(cur[j].z, cur[j].w);
 #pragma unroll
-                    for (int k = 0; k < kBGK; ++k) {
+                    for (int k = 0; k < KM; ++k) {
                         const float b = sb[k][min(q0 + j, kBGPix - 1)];
-                        acc[k].x = fmaf(b, cur[j].x, acc[k].x);
-                        acc[k].y = fmaf(b, cur[j].y, acc[k].y);
-                        acc[k].z = fmaf(b, cur[j].z, acc[k].z);
-                        acc[k].w = fmaf(b, cur[j].w, acc[k].w);
+                        const uint64_t bb = bg_pack2(b, b);
+                        acc[k][0] = bg_fma2(bb, y01, acc[k][0]);
+                        acc[k][1] = bg_fma2(bb, y23, acc[k][1]);
                     }
                 }
 #pragma unroll
@@ -64,8 +82,13 @@ bg_project_t_kernel(const float* __restrict__ yt, int64_t ld, int64_t d, const f
     if (f < ld) {
         float* out = part + (int64_t)blockIdx.y * k_n * ld + f;
 #pragma unroll
-        for (int k = 0; k < kBGK; ++k)
-            if (k < k_n) *reinterpret_cast<float4*>(out + (int64_t)k * ld) = acc[k];
+        for (int k = 0; k < KM; ++k)
+            if (k < k_n) {
+                float4 a;
+                bg_unpack2(acc[k][0], a.x, a.y);
+                bg_unpack2(acc[k][1], a.z, a.w);
+                *reinterpret_cast<float4*>(out + (int64_t)k * ld) = a;
+            }
     }
 }
 
@@ -75,10 +98,13 @@ bg_remove_t_kernel(float* __restrict__ yt, int64_t ld, int64_t d, const float* _
     __shared__ float sb[kBGK][kBGPix];
     const int64_t f = ((int64_t)blockIdx.x * kBGThreads + threadIdx.x) * 4;
     const int64_t p0 = (int64_t)blockIdx.y * pix_per_cta, p1 = min(d, p0 + pix_per_cta);
-    float4 v[kBGK];
+    uint64_t v[kBGK][2];
 #pragma unroll
-    for (int k = 0; k < kBGK; ++k)
-        v[k] = (k < k_n && f < ld) ? *reinterpret_cast<const float4*>(vbg + (int64_t)k * ld + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < kBGK; ++k) {
+        const float4 t = (k < k_n && f < ld) ? *reinterpret_cast<const float4*>(vbg + (int64_t)k * ld + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[k][0] = bg_pack2(t.x, t.y);
+        v[k][1] = bg_pack2(t.z, t.w);
+    }
     for (int64_t pb = p0; pb < p1; pb += kBGPix) {
         const int n = (int)min((int64_t)kBGPix, p1 - pb);
         __syncthreads();
@@ -102,15 +128,17 @@ bg_remove_t_kernel(float* __restrict__ yt, int64_t ld, int64_t d, const float* _
 #pragma unroll
                 for (int j = 0; j < kBGBatch; ++j) {
                     if (q0 + j < n) {
-                        float4 y = cur[j];
+                        uint64_t y01 = bg_pack2(cur[j].x, cur[j].y), y23 = bg_pack2(cur[j].z, cur[j].w);
 #pragma unroll
                         for (int k = 0; k < kBGK; ++k) {
                             const float b = -sb[k][q0 + j];
-                            y.x = fmaf(b, v[k].x, y.x);
-                            y.y = fmaf(b, v[k].y, y.y);
-                            y.z = fmaf(b, v[k].z, y.z);
-                            y.w = fmaf(b, v[k].w, y.w);
+                            const uint64_t bb = bg_pack2(b, b);
+                            y01 = bg_fma2(bb, v[k][0], y01);
+                            y23 = bg_fma2(bb, v[k][1], y23);
                         }
+                        float4 y;
+                        bg_unpack2(y01, y.x, y.y);
+                        bg_unpack2(y23, y.z, y.w);
                         *reinterpret_cast<float4*>(dst + (int64_t)(q0 + j) * ld) = y;
                     }
                 }
@@ -127,12 +155,14 @@ extern "C" int pmd_bg_project_t(const float* yt, int64_t ld, int64_t d, const fl
                                 void* stream) {
     const char* fn = "pmd_bg_project_t";
     PMD_REQUIRE(yt && bg && part, fn, "null pointer");
-    PMD_REQUIRE(ld > 0 && ld % 4 == 0 && d > 0 && k > 0 && k <= pmd::kBGK && n_ranges > 0 && n_ranges <= 65535, fn,
-                "bad size (ld multiple of 4, 1 <= k <= 16)");
+    PMD_REQUIRE(ld > 0 && ld % 4 == 0 && d > 0 && k > 0 && k <= 32 && n_ranges > 0 && n_ranges <= 65535, fn,
+                "bad size (ld multiple of 4, 1 <= k <= 32)");
     PMD_REQUIRE(((uintptr_t)yt % 16) == 0 && ((uintptr_t)part % 16) == 0, fn, "operands must be 16-byte aligned");
     const int64_t per = (d + n_ranges - 1) / n_ranges;
     dim3 grid((unsigned)((ld / 4 + pmd::kBGThreads - 1) / pmd::kBGThreads), (unsigned)n_ranges);
-    pmd::bg_project_t_kernel<<<grid, pmd::kBGThreads, 0, (cudaStream_t)stream>>>(yt, ld, d, bg, (int)k, per, part);
+    if (k <= 16) pmd::bg_project_t_kernel<16><<<grid, pmd::kBGThreads, 0, (cudaStream_t)stream>>>(yt, ld, d, bg, (int)k, per, part);
+    else if (k <= 26) pmd::bg_project_t_kernel<26><<<grid, pmd::kBGThreads, 0, (cudaStream_t)stream>>>(yt, ld, d, bg, (int)k, per, part);
+    else pmd::bg_project_t_kernel<32><<<grid, pmd::kBGThreads, 0, (cudaStream_t)stream>>>(yt, ld, d, bg, (int)k, per, part);
     return pmd::check_launch(fn);
 }
 

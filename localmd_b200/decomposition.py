@@ -203,14 +203,32 @@ def background_basis(movie: DeviceMovie, mean, std, bg_frames, bg_sketch, backgr
     """pmd_loader.py:300-314 + 46-68: rSVD of <= 1000 standardised frames -> (K, d) orthonormal rows.
     With a process group the sampled frames are fetched from their owner ranks; every rank computes the same basis."""
     dev = movie.device
-    raw = sharding.gather_frames(movie, bg_frames, group, bounds)
-    a_t = ops.standardize_frames(raw, torch.arange(raw.shape[0], device=dev), mean, std)  # (n, d) = A^T
-    y = torch.matmul(a_t.t(), bg_sketch).contiguous()  # (d, l)
-    q = ops.orthonormalize_cols(y[None])[0]  # (d, l)
-    bmat = torch.matmul(q.t(), a_t.t()).contiguous()  # (l, n)
+    l = bg_sketch.shape[1]
+    if l > 32:   # wider sketches than the streaming kernels take (background_rank > 22): library contractions
+        raw = sharding.gather_frames(movie, bg_frames, group, bounds)
+        a_t = ops.standardize_frames(raw, torch.arange(raw.shape[0], device=dev), mean, std)  # (n, d) = A^T
+        with ops.fp32_matmul():
+            y = torch.matmul(a_t.t(), bg_sketch).contiguous()  # (d, l)
+            q = ops.orthonormalize_cols(y[None])[0]  # (d, l)
+            bmat = torch.matmul(q.t(), a_t.t()).contiguous()  # (l, n)
+            _, e = ops.jacobi_eigh(ops.gram_rows(bmat[None]), mode=0)
+            u = torch.matmul(q, e[0][:, :background_rank])  # (d, K)
+        return u.t().contiguous()
+    # the sampled frames, standardised, in the pixel-major layout (d, ld): both contractions of the rSVD stream it once
+    n = len(bg_frames)
+    if group is None:
+        movie2d, idx = movie.frame_source(bg_frames)   # the resident movie itself + row indices: no gathered copy
+    else:
+        movie2d, idx = sharding.gather_frames(movie, bg_frames, group, bounds), torch.arange(n, device=dev)
+    yt = ops.standardize_frames_t(movie2d, idx, mean, std, ld=(n + 31) // 32 * 32)   # (d, ld), 128-byte aligned rows
+    y = ops.rows_sketch(yt, n, bg_sketch.contiguous())                # (d, l) = A Omega               (pmd_loader.py:58)
+    for _ in range(2):                                                # orthonormal basis of its range (pmd_loader.py:59)
+        y = ops.rows_times_small(y[None], ops.chol_whiten(ops.gram_cols(y[None], l)))[0]   # CholQR2, float64 Gram
+    qt = ops.rows_times_small(y[None], torch.eye(l, dtype=torch.float32, device=dev)[None], transposed=True)[0]   # (l, d) = Q^T
+    bmat = ops.bg_project_t(yt, qt, n_ranges=296)[:, :n].contiguous()  # (l, n) = Q^T A                (pmd_loader.py:60)
     _, e = ops.jacobi_eigh(ops.gram_rows(bmat[None]), mode=0)
-    u = torch.matmul(q, e[0][:, :background_rank])  # (d, K)
-    return u.t().contiguous()
+    # left singular vectors of A restricted to the leading `background_rank` (pmd_loader.py:61-68), as rows (K, d)
+    return ops.rows_times_small(y[None], e[:, :, :background_rank].contiguous(), transposed=True)[0]
 
 
 def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, chunk=None, defer=False):
@@ -255,10 +273,25 @@ def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, 
         tp.append(ts.reshape(-1))
     sp, tp = torch.cat(sp), torch.cat(tp)
 
-    def finish():
+    if not defer:
         return np.percentile(sp.cpu().numpy().flatten(), sim_conf), np.percentile(tp.cpu().numpy().flatten(), sim_conf)
+    # deferred: the statistics travel to page-locked host memory on the CURRENT (side) stream; the percentiles are taken
+    # when the thresholds are first needed -- at the rank decision at the end of the block stage, by which time the host has
+    # long run ahead of the device, so neither the copy nor the host-side percentile stalls the main stream
+    host = [torch.empty(x.shape, dtype=x.dtype, pin_memory=True) for x in (sp, tp)]
+    for h, x in zip(host, (sp, tp)):
+        h.copy_(x, non_blocking=True)
+    done = torch.cuda.Event()
+    done.record(torch.cuda.current_stream(device))
+    memo = []
 
-    return finish if defer else finish()
+    def finish():
+        if not memo:
+            done.synchronize()
+            memo.append((float(np.percentile(host[0].numpy().flatten(), sim_conf)), float(np.percentile(host[1].numpy().flatten(), sim_conf))))
+        return memo[0]
+
+    return finish
 
 
 def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_t, mcf, sketches, spatial_denoiser=None,
@@ -380,6 +413,8 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
     v = torch.bmm(lmat.transpose(1, 2), vn)  # (nb, r, ld)
     del uf, vn
     _submark("blocks.bmm_uv")
+    if callable(thr_s):   # deferred threshold simulation (see simulate_thresholds): resolved here, where it is first needed
+        thr_s, thr_t = thr_s()
     sstat, tstat, ranks = ops.block_stats_rank(u, v, bh, bw, r, thr_s, thr_t, mcf, t=t)
     _submark("blocks.stats")
     return u, v, ranks, sstat, tstat
@@ -407,6 +442,8 @@ def block_decompositions_windowed(yt, t, d2, starts_dev, bh, bw, r, taf, saf, th
     (single_residual_block_md, 333-387: time average only, no spatial pooling); a block stops once it holds r
     components.  sketches: list over windows of (nb, window // taf, r + 10).  Same return values as
     block_decompositions, with V = (kept U)^T block over all t frames (get_temporal_projector, 390-407)."""
+    if callable(thr_s):
+        thr_s, thr_t = thr_s()
     dev = yt.device
     d, ld = yt.shape
     nb = starts_dev.shape[0]
@@ -988,8 +1025,7 @@ def localmd_decomposition(
         if thr is not None:
             thr_s, thr_t = float(thr[0]), float(thr[1])
         elif thr_pending is not None and thr_pending[1:] == (bh, bw, window_chunks):
-            torch.cuda.current_stream(dev).wait_stream(side_thr)
-            thr_s, thr_t = thr_pending[0]()
+            thr_s = thr_t = thr_pending[0]   # callable, resolved at the rank decision of the block stage
         else:
             thr_s, thr_t = simulate_thresholds(bh, bw, window_chunks, sim_conf, draws, gen, dev)
         tm.mark("thresholds")
@@ -1207,7 +1243,7 @@ def localmd_decomposition(
         _ACTIVE_TIMER = None
         if details is not None:
             details.update(
-                ranks=ranks_host.astype(np.int32), block_starts=[tuple(x) for x in starts.tolist()], thresholds=(thr_s, thr_t),
+                ranks=ranks_host.astype(np.int32), block_starts=[tuple(x) for x in starts.tolist()], thresholds=thr_s() if callable(thr_s) else (thr_s, thr_t),
                 spatial_basis=np.stack([img.reshape(-1, order=order) for img in bg.cpu().numpy().reshape(-1, d1, d2)], axis=1),
                 sstat=sstat.cpu().numpy(), tstat=tstat.cpu().numpy(), mixing=p.cpu().numpy(), v_init=v_init.cpu().numpy(),
                 v_full=v_full.cpu().numpy(), frames=frames, h2d_bytes=movie.h2d_bytes,

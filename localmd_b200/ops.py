@@ -185,8 +185,40 @@ def standardize_frames_t(movie2d, frames, mean, stdv, ld=None):
     return out
 
 
+def rows_sketch(yt, n, omega):
+    """y (d, l) = yt[:, :n] @ omega for the pixel-major standardised frames yt (d, ld) and a sketch matrix omega (n, l),
+    l <= 32 (pmd_loader.py:58, the random projection of the background rSVD)."""
+    _req(yt, torch.float32, "yt"), _req(omega, torch.float32, "omega")
+    d, ld = yt.shape
+    l = omega.shape[1]
+    y = torch.empty((d, l), dtype=torch.float32, device=yt.device)
+    _call("pmd_rows_sketch", _p(yt), ld, d, int(n), _p(omega), l, _p(y), l, _stream())
+    return y
+
+
+def chol_whiten(g):
+    """(batch, n, n) float64 Gram matrices -> (batch, n, n) float32 L^-T of their Cholesky factors, n <= 32."""
+    _req(g, torch.float64, "g")
+    b, n, _ = g.shape
+    t = torch.empty((b, n, n), dtype=torch.float32, device=g.device)
+    _call("pmd_chol_whiten", _p(g), b, n, _p(t), _stream())
+    return t
+
+
+def rows_times_small(x, m, ncols=None, transposed=False):
+    """x (batch, d, ldx)[:, :, :k] @ m (batch, k, nc) with k, nc <= 32 -> (batch, d, nc), or (batch, nc, d) when
+    `transposed`.  k = m.shape[1]."""
+    _req(x, torch.float32, "x"), _req(m, torch.float32, "m")
+    b, d, ldx = x.shape
+    k, nc = m.shape[1], (m.shape[2] if ncols is None else int(ncols))
+    out = torch.empty((b, nc, d) if transposed else (b, d, nc), dtype=torch.float32, device=x.device)
+    _call("pmd_rows_times_small", _p(x), ldx, d, k, _p(m), m.shape[2], nc, _p(out), d if transposed else nc, int(bool(transposed)),
+          b, d * ldx, k * m.shape[2], d * nc, _stream())
+    return out
+
+
 def bg_project_t(yt, bg, n_ranges=128):
-    """vbg (K, ld) = bg (K, d) @ yt (d, ld) for the pixel-major init movie, K <= 16 (deterministic two-stage sum)."""
+    """vbg (K, ld) = bg (K, d) @ yt (d, ld) for the pixel-major init movie, K <= 32 (deterministic two-stage sum)."""
     _req(yt, torch.float32, "yt"), _req(bg, torch.float32, "bg")
     d, ld = yt.shape
     k = bg.shape[0]

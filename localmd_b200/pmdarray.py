@@ -26,11 +26,8 @@ class PMDArray:
         self._r = np.asarray(r)
         self._s = np.asarray(s)
         self._v = np.asarray(v)
-        self.mean_img = np.asarray(mean_img)
-        self.var_img = np.asarray(std_img)
-        d = self.fov_dim1 * self.fov_dim2
-        self.row_indices = np.arange(d).reshape((self.fov_dim1, self.fov_dim2), order=self.order)
-        self._phys_indices = np.arange(d).reshape((self.fov_dim1, self.fov_dim2))
+        self._mean_img = np.asarray(mean_img)
+        self._var_img = np.asarray(std_img)
         self._device = device
         self._dev = None
         self._lazy = None
@@ -46,15 +43,37 @@ class PMDArray:
         d = self.fov_dim1 * self.fov_dim2
         self._u = self._r = self._s = self._v = None
         self._lazy = dict(csr=csr_order, r=rmix, s=s, v=vt, n_cols=int(rmix.shape[0]))
-        self.mean_img = mean.cpu().numpy().reshape(self.fov_dim1, self.fov_dim2)
-        self.var_img = std.cpu().numpy().reshape(self.fov_dim1, self.fov_dim2)
-        self.row_indices = np.arange(d).reshape((self.fov_dim1, self.fov_dim2), order=self.order)
-        self._phys_indices = np.arange(d).reshape((self.fov_dim1, self.fov_dim2))
+        self._mean_img = self._var_img = None      # host images: materialised on first access, like the factors
         self._device = device
         ip, ix, v32 = csr_phys32
         self._dev = dict(device=torch.device(device), indptr=ip, indices=ix, values=v32,
                          rs=(rmix * s[None, :]).contiguous(), vt=vt.contiguous(), mean=mean.contiguous(), std=std.contiguous())
         return self
+
+    @property
+    def mean_img(self):
+        if self._mean_img is None:
+            self._mean_img = self._to_host(self._dev["mean"]).reshape(self.fov_dim1, self.fov_dim2)
+        return self._mean_img
+
+    @property
+    def var_img(self):
+        if self._var_img is None:
+            self._var_img = self._to_host(self._dev["std"]).reshape(self.fov_dim1, self.fov_dim2)
+        return self._var_img
+
+    @property
+    def row_indices(self):
+        """(d1, d2) array: row of U (numbered in `order`) of every pixel (pmdarray.py:37-38)."""
+        if getattr(self, "_row_indices", None) is None:
+            self._row_indices = np.arange(self.fov_dim1 * self.fov_dim2).reshape((self.fov_dim1, self.fov_dim2), order=self.order)
+        return self._row_indices
+
+    @property
+    def _phys_indices(self):
+        if getattr(self, "_phys", None) is None:
+            self._phys = np.arange(self.fov_dim1 * self.fov_dim2).reshape((self.fov_dim1, self.fov_dim2))
+        return self._phys
 
     @staticmethod
     def _to_host(t):

@@ -33,3 +33,20 @@ for lib in ("cusolver", "magma"):
         timeit("eigh f64 (%s)" % lib, lambda: torch.linalg.eigh(g))
     except Exception as exc:
         print(lib, "unavailable:", exc)
+torch.backends.cuda.preferred_linalg_library("cusolver")
+for n in (412, 825, 1100):
+    gs = g[:n, :n].contiguous()
+    timeit("eigh f64 n=%d" % n, lambda: torch.linalg.eigh(gs))
+gs = [g[i * 412:(i + 1) * 412, i * 412:(i + 1) * 412].contiguous() for i in range(4)]
+ss = [torch.cuda.Stream() for _ in range(4)]
+def four():
+    cur = torch.cuda.current_stream()
+    for s, m in zip(ss, gs):
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):
+            torch.linalg.eigh(m)
+    for s in ss:
+        cur.wait_stream(s)
+timeit("4 x eigh f64 n=412 on 4 streams", four)
+gb = torch.stack(gs)
+timeit("batched eigh f64 4 x 412", lambda: torch.linalg.eigh(gb))

@@ -664,3 +664,90 @@ def test_bg_filter_t(ops, d, t, K):
     ref_y = yt.astype(np.float64) - bg.T.astype(np.float64) @ vbg.cpu().numpy().astype(np.float64)
     np.testing.assert_allclose(ytd.cpu().numpy(), ref_y, rtol=0, atol=1e-5)
     assert np.all(ytd.cpu().numpy()[:, t:] == 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,n,l", [(700, 1000, 25), (333, 130, 11), (64, 1500, 32), (5000, 37, 16)])
+def test_rows_sketch(ops, d, n, l):
+    """y = yt[:, :n] @ omega on the pixel-major frames (csrc/bgbasis.cu) against a float64 matmul; padding columns of yt
+    hold garbage and must not leak into the result."""
+    rng = np.random.default_rng(d + n)
+    ld = (n + 3) // 4 * 4 + 4
+    yt = rng.standard_normal((d, ld)).astype(np.float32)
+    yt[:, n:] = np.nan
+    om = rng.standard_normal((n, l)).astype(np.float32)
+    y = ops.rows_sketch(dev(yt), n, dev(om)).cpu().numpy()
+    ref = yt[:, :n].astype(np.float64) @ om.astype(np.float64)
+    np.testing.assert_allclose(y, ref, rtol=0, atol=3e-6 * np.abs(ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch,d,ldx,k,nc,transposed", [(1, 1000, 25, 25, 25, False), (1, 777, 28, 25, 15, True), (3, 130, 32, 32, 32, False),
+                                                          (2, 65, 7, 5, 3, True)])
+def test_rows_times_small(ops, batch, d, ldx, k, nc, transposed):
+    rng = np.random.default_rng(d + k)
+    x = rng.standard_normal((batch, d, ldx)).astype(np.float32)
+    m = rng.standard_normal((batch, k, nc)).astype(np.float32)
+    out = ops.rows_times_small(dev(x), dev(m), transposed=transposed).cpu().numpy()
+    ref = np.einsum("bpj,bjc->bpc", x[:, :, :k].astype(np.float64), m.astype(np.float64))
+    if transposed:
+        ref = ref.transpose(0, 2, 1)
+    np.testing.assert_allclose(out, ref, rtol=0, atol=2e-6 * np.abs(ref).max())
+
+
+@pytest.mark.gpu
+def test_bg_project_t_wide(ops):
+    """The coefficient pass of the background rSVD: pmd_bg_project_t with 17 <= k <= 32 rows."""
+    rng = np.random.default_rng(3)
+    d, t, K = 3000, 1000, 25
+    yt = rng.standard_normal((d, t)).astype(np.float32)
+    q = np.linalg.qr(rng.standard_normal((d, K)))[0].T.astype(np.float32)
+    v = ops.bg_project_t(dev(yt), dev(q), n_ranges=11).cpu().numpy()
+    ref = q.astype(np.float64) @ yt.astype(np.float64)
+    np.testing.assert_allclose(v, ref, rtol=0, atol=2e-5 * np.abs(ref).max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [3, 15])
+def test_background_basis_matches_oracle(ops, K):
+    """background_basis (standardise + transpose, streaming sketch, CholQR-style orthonormalisation, coefficient pass,
+    rotation) spans the same subspace as the oracle's randomised SVD with the same sketch matrix (pmd_loader.py:46-68)."""
+    import oracle.pmd_oracle as O
+    from localmd_b200 import decomposition as D
+    from localmd_b200.dataset import DeviceMovie
+
+    from synth import make_movie
+
+    T, d1, d2 = 600, 24, 28
+    movie = make_movie(T, d1, d2, n_cells=6, seed=2)
+    rng = np.random.default_rng(K)
+    frames = sorted(rng.choice(T, 200, replace=False).tolist())
+    sketch = rng.standard_normal((len(frames), K + 10)).astype(np.float32)
+    dm = DeviceMovie(movie, torch.device("cuda"))
+    mean, std = D.compute_mean_and_noise(dm)
+    bg = D.background_basis(dm, mean, std, frames, dev(sketch), K).cpu().numpy()     # (K, d)
+    assert bg.shape == (K, d1 * d2)
+    np.testing.assert_allclose(bg @ bg.T, np.eye(K), atol=2e-5)
+    with O.precision(np.float64):
+        u = O.background_basis(movie, mean.cpu().numpy().reshape(d1, d2), std.cpu().numpy().reshape(d1, d2), frames, sketch, K,
+                               order="C").astype(np.float64)                                # (d, K), physical pixel order
+    sv = np.linalg.svd(bg.astype(np.float64) @ u, compute_uv=False)
+    assert np.arccos(np.clip(sv.min(), -1, 1)) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,batch", [(25, 1), (32, 3), (5, 2)])
+def test_chol_whiten(ops, n, batch):
+    """x @ L^-T is orthonormal for g = x^T x = L L^T; a dependent column gives a zero column."""
+    rng = np.random.default_rng(n)
+    x = rng.standard_normal((batch, 400, n)) * np.logspace(0, -3, n)[None, None, :]
+    x[-1, :, n - 2] = x[-1, :, 0] * 2.0 - x[-1, :, 1]          # dependent column in the last matrix
+    g = np.einsum("bmi,bmj->bij", x, x)
+    t = ops.chol_whiten(dev(g, torch.float64)).cpu().numpy().astype(np.float64)
+    q = np.einsum("bmi,bij->bmj", x, t)
+    qq = np.einsum("bmi,bmj->bij", q, q)
+    want = np.stack([np.eye(n)] * batch)
+    want[-1, n - 2, n - 2] = 0.0
+    np.testing.assert_allclose(qq, want, atol=5e-5)
+    assert np.all(t[-1][:, n - 2] == 0)
+    assert np.allclose(np.tril(t[0], -1), 0)

@@ -137,33 +137,34 @@ rows_sketch_kernel(const float* __restrict__ yt, int64_t ld, int64_t d, int64_t 
     }
 }
 
-// out[p][c] = sum_j x[p][j] m[j][c]   (j < k <= 32, c < nc <= 32); out may be written transposed (out_t[c][p]).
-// One thread per row: the row of x lives in registers, m in shared memory (broadcast reads).
+// out[p][c] = sum_j x[p][j] m[j][c]   (j < k <= KM, c < nc <= KM; KM = 32); out may be written transposed
+// (out_t[c][p]).  One thread per row: the row of x lives in registers, m in shared memory (broadcast reads).
 constexpr int kRTThreads = 128;
 
+template <int KM>
 __global__ void __launch_bounds__(kRTThreads)
 rows_times_small_kernel(const float* __restrict__ x, int64_t ldx, int64_t d, int k, const float* __restrict__ m, int64_t ldm, int nc,
                         float* __restrict__ out, int64_t ldo, int transposed, int64_t batch_stride_x, int64_t batch_stride_m,
                         int64_t batch_stride_o) {
-    __shared__ float sm[kRSL * kRSL];
+    __shared__ float sm[KM * KM];
     const int64_t b = blockIdx.y;
     x += b * batch_stride_x;
     m += b * batch_stride_m;
     out += b * batch_stride_o;
-    for (int i = threadIdx.x; i < kRSL * kRSL; i += kRTThreads) {
-        const int j = i / kRSL, c = i - j * kRSL;
+    for (int i = threadIdx.x; i < KM * KM; i += kRTThreads) {
+        const int j = i / KM, c = i - j * KM;
         sm[i] = (j < k && c < nc) ? m[(int64_t)j * ldm + c] : 0.f;
     }
     __syncthreads();
     const int64_t p = (int64_t)blockIdx.x * kRTThreads + threadIdx.x;
     if (p >= d) return;
-    float xr[kRSL];
+    float xr[KM];
 #pragma unroll
-    for (int j = 0; j < kRSL; ++j) xr[j] = j < k ? x[p * ldx + j] : 0.f;
+    for (int j = 0; j < KM; ++j) xr[j] = j < k ? x[p * ldx + j] : 0.f;
     for (int c = 0; c < nc; ++c) {
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < kRSL; ++j) s = fmaf(xr[j], sm[j * kRSL + c], s);
+        for (int j = 0; j < KM; ++j) s = fmaf(xr[j], sm[j * KM + c], s);
         if (transposed) out[(int64_t)c * ldo + p] = s;
         else out[p * ldo + c] = s;
     }
@@ -256,13 +257,11 @@ extern "C" int pmd_rows_times_small(const float* x, int64_t ldx, int64_t d, int6
                                     int64_t batch_stride_m, int64_t batch_stride_o, void* stream) {
     const char* fn = "pmd_rows_times_small";
     PMD_REQUIRE(x && m && out, fn, "null pointer");
-    PMD_REQUIRE(d > 0 && k > 0 && k <= pmd::kRSL && nc > 0 && nc <= pmd::kRSL && ldx >= k && ldm >= nc, fn,
-                "bad size (k, nc <= 32)");
+    PMD_REQUIRE(d > 0 && k > 0 && k <= 32 && nc > 0 && nc <= 32 && ldx >= k && ldm >= nc, fn, "bad size (k, nc <= 32)");
     PMD_REQUIRE(batch > 0 && batch <= 65535, fn, "batch must be in 1..65535");
     PMD_REQUIRE(x != out, fn, "in-place operation is not supported");
     dim3 grid((unsigned)((d + pmd::kRTThreads - 1) / pmd::kRTThreads), (unsigned)batch);
-    pmd::rows_times_small_kernel<<<grid, pmd::kRTThreads, 0, (cudaStream_t)stream>>>(x, ldx, d, (int)k, m, ldm, (int)nc, out, ldo,
-                                                                                  transposed, batch_stride_x, batch_stride_m,
-                                                                                  batch_stride_o);
+    pmd::rows_times_small_kernel<32><<<grid, pmd::kRTThreads, 0, (cudaStream_t)stream>>>(
+        x, ldx, d, (int)k, m, ldm, (int)nc, out, ldo, transposed, batch_stride_x, batch_stride_m, batch_stride_o);
     return pmd::check_launch(fn);
 }

@@ -409,8 +409,11 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
     _submark("blocks.jacobi2")
     lpad = torch.zeros((nb, rp, rp), dtype=torch.float32, device=dev)
     lpad[:, :r, :r] = lmat
-    u = torch.bmm(uf, lpad)  # (nb, b, rp)
-    v = torch.bmm(lmat.transpose(1, 2), vn)  # (nb, r, ld)
+    # rotation into the singular vectors (decomposition.py:319-323): library SIMT batched GEMMs, pinned to full float32 (a
+    # hand-written packed-FMA kernel measured 2.8 ms against the library's 2.3 ms at C2 and was dropped)
+    with ops.fp32_matmul():
+        u = torch.bmm(uf, lpad)  # (nb, b, rp)
+        v = torch.bmm(lmat.transpose(1, 2), vn)  # (nb, r, ld)
     del uf, vn
     _submark("blocks.bmm_uv")
     if callable(thr_s):   # deferred threshold simulation (see simulate_thresholds): resolved here, where it is first needed
@@ -547,13 +550,11 @@ class SparseU:
         self._tc_host = None
         self._ts_host = None
         self._ts_future = None
+        self._utu_future = None
+        self._tables_started = False
         which = os.environ.get("PMD_K7", "ts")   # development switch between the generations of the projection kernel
-        if regular and which == "ts":
-            # K7 with TMA-fed raw tiles and the movie operand in tensor memory (csrc/project_ts.cu): host tables now
-            # (native library), device tables and coefficient images at the first projection call
-            # the native routine releases the GIL: it runs on a worker thread while this thread enqueues the whitening
-            self._ts_future = _HOST_POOL.submit(ops.make_strips_ts, rows, cols, bh, bw, d1, d2, ranks_host.copy(), self.col0_host.copy(),
-                                                bg.shape[0])
+        self._want_ts = bool(regular and which == "ts")
+        if self._want_ts:
             self._ts_host = True   # placeholder until the first projection call collects the result
         if regular and self._ts_host is None and which != "simt":
             # K7 on the tensor cores (csrc/project_tc.cu): host tables now (native library), device tables and
@@ -563,6 +564,23 @@ class SparseU:
             self._build_simt_strips()
         if self.strips is None and self._tc_host is None and self._ts_host is None:
             self._build_supertiles()
+
+    def start_host_tables(self):
+        """Hand the host-side tables to the worker thread (idempotent): the block-pair bookkeeping of U^T U (whitening,
+        NumPy) and the strip tables of K7 (native routine of the library, releases the GIL).  The driver calls this AFTER
+        it has enqueued the prune-sketch GEMMs, so that the worker's GIL-holding NumPy steps compete with a main thread
+        that has device work queued, not with one the device is waiting for."""
+        if self._tables_started:
+            return
+        self._tables_started = True
+        if self.n_local > 0:
+            self._utu_future = _HOST_POOL.submit(ops.utu_host_tables, self.starts, self.bh, self.bw, self.ranks_host.copy())
+        if self._want_ts:
+            # K7 with TMA-fed raw tiles and the movie operand in tensor memory (csrc/project_ts.cu): host tables on the worker,
+            # device tables and coefficient images at the first projection call
+            rows, cols = self._regular
+            self._ts_future = _HOST_POOL.submit(ops.make_strips_ts, rows, cols, self.bh, self.bw, self.d1, self.d2,
+                                                self.ranks_host.copy(), self.col0_host.copy(), self.bg.shape[0])
 
     def _build_supertiles(self):
         """Tables of the supertile kernel (irregular block lists, geometries neither strip kernel supports)."""
@@ -666,15 +684,19 @@ class SparseU:
         """U^T U in float64 as (CSR of the local x local part, C = U^T bg^T (n_cols, K)): the two sparse products
         of decomposition.py:974-981 reduce to applying these to the right factor."""
         if getattr(self, "_gram", None) is None:
+            self.start_host_tables()
             dev = self.uvals64.device
             bg64 = self.bg.to(torch.float64).contiguous()
             blk_of_col = torch.repeat_interleave(
-                torch.arange(len(self.ranks_host), device=dev, dtype=torch.int32), self.ranks_dev.to(torch.int64)).contiguous()
+                torch.arange(len(self.ranks_host), device=dev, dtype=torch.int32), self.ranks_dev.to(torch.int64),
+                output_size=self.n_local).contiguous()
             c = ops.project_cols_f64(bg64, self.d2, self.starts_dev, self.bh, self.bw, blk_of_col, self.col0_dev, self.uvals64,
                                      bg64)  # (n_cols, K)
             if self.n_local > 0:
+                host = self._utu_future.result() if self._utu_future is not None else None
+                self._utu_future = None
                 csr = ops.utu_local_csr(self.starts, self.starts_dev, self.bh, self.bw, self.ranks_host, self.ranks_dev,
-                                        self.col0_host, self.col0_dev, self.uvals64)
+                                        self.col0_host, self.col0_dev, self.uvals64, host=host)
             else:
                 csr = None
             self._gram = (csr, c)
@@ -715,6 +737,7 @@ class SparseU:
     def project(self, movie2d, mean, inv_std, z):
         """z[:, :n] (R, ldz) (+)= U^T standardised(movie2d)   (K7a + K7b)."""
         n = movie2d.shape[0]
+        self.start_host_tables()
         if self._ts_future is not None:
             self._ts_host = self._ts_future.result()
             self._ts_future = None
@@ -790,9 +813,13 @@ def compute_lowrank_factorized_svd(u, v, only_left=False, factor="eigh"):
         chol, info = torch.linalg.cholesky_ex(g)
         dg = torch.diagonal(chol)
         ok = (info == 0) & (dg.min() > 1e-6 * dg.max())  # cond(G) < ~1e12 : safe in float64
+        # the triangular solve is enqueued before the verdict is read back (the read is a host synchronisation; the device
+        # keeps working through it) and discarded in the rare singular case
+        spec = torch.linalg.solve_triangular(chol, right.t(), upper=False).t()
         if bool(ok.item()):
-            mix64 = torch.linalg.solve_triangular(chol, right.t(), upper=False).t()
+            mix64 = spec
             _submark("whiten.chol")
+        del spec
     if mix64 is None:
         vals, vecs = sym_eigh_desc_abs(g)
         _submark("whiten.eigh")
@@ -1043,8 +1070,6 @@ def localmd_decomposition(
         r = int(max_components)
         if r + 10 > 112:
             raise ValueError("max_components > 102 is not supported by the sm_100a Jacobi kernel")
-        if r > 64:
-            raise ValueError("max_components > 64 is not supported by the sm_100a block kernels")
         dim_1_iters, dim_2_iters = tile_starts(d1, bh), tile_starts(d2, bw)
         starts = np.stack(np.meshgrid(dim_1_iters, dim_2_iters, indexing="ij"), axis=-1).reshape(-1, 2).astype(np.int32)
         nb = starts.shape[0]
@@ -1104,6 +1129,18 @@ def localmd_decomposition(
         # block origins relative to the rows of the init movie this rank holds
         starts_fit = starts_dev if row_lo == 0 else (starts_dev - torch.tensor([row_lo, 0], dtype=torch.int32, device=dev))
         block_weights = pyramid_weights(bh, bw)
+        # summed pyramid weights of the covering blocks: sum_b shift(block_weights) = Rm^T W Cm with the 0/1
+        # incidence matrices of (block-local row, FOV row) and (block-local column, FOV column); exact in float64.
+        # (Rank independent: computed and uploaded here, while the device is busy with the init filter, not after the
+        # rank decision, where the device would wait for the host.)
+        rm, cm = np.zeros((bh, d1)), np.zeros((bw, d2))
+        for q in range(bh):
+            rm[q, np.asarray(dim_1_iters) + q] = 1.0
+        for q in range(bw):
+            cm[q, np.asarray(dim_2_iters) + q] = 1.0
+        cumw = rm.T @ block_weights.astype(np.float64) @ cm
+        block_weights_dev = torch.from_numpy(block_weights.reshape(-1)).to(dev)
+        cumw_dev = torch.from_numpy(cumw.reshape(-1)).to(dev)
 
         # ---- block fits (decomposition.py:790-838) -------------------------------------------------
         bs = take("block_sketches")
@@ -1145,23 +1182,15 @@ def localmd_decomposition(
         tm.mark("blocks")
 
         # ---- weighted sparse assembly (decomposition.py:811-857) -----------------------------------
-        # summed pyramid weights of the covering blocks: sum_b shift(block_weights) = Rm^T W Cm with the 0/1
-        # incidence matrices of (block-local row, FOV row) and (block-local column, FOV column); exact in float64
-        rm, cm = np.zeros((bh, d1)), np.zeros((bw, d2))
-        for q in range(bh):
-            rm[q, np.asarray(dim_1_iters) + q] = 1.0
-        for q in range(bw):
-            cm[q, np.asarray(dim_2_iters) + q] = 1.0
-        cumw = rm.T @ block_weights.astype(np.float64) @ cm
         # this rank's kept components: weighted values (float64 + float32) and temporal traces
         ranks_loc_host = ranks_host[b0:b1]
         col0_loc = torch.from_numpy(np.concatenate([[0], np.cumsum(ranks_loc_host)[:-1]]).astype(np.int64)).to(dev)
         ncol_loc = int(ranks_loc_host.sum())
         uv64, uv32 = ops.assemble_u(
-            u_blk, bh, bw, starts_dev[b0:b1].contiguous(), ranks_loc, col0_loc, torch.from_numpy(block_weights.reshape(-1)).to(dev),
-            torch.from_numpy(cumw.reshape(-1)).to(dev), d2, ncol_loc,
+            u_blk, bh, bw, starts_dev[b0:b1].contiguous(), ranks_loc, col0_loc, block_weights_dev, cumw_dev, d2, ncol_loc,
         )
-        blk_of_col = torch.repeat_interleave(torch.arange(b1 - b0, device=dev), ranks_loc.to(torch.int64))
+        # (output_size: without it repeat_interleave reads the total back from the device -- a host synchronisation)
+        blk_of_col = torch.repeat_interleave(torch.arange(b1 - b0, device=dev), ranks_loc.to(torch.int64), output_size=ncol_loc)
         comp_of_col = torch.arange(ncol_loc, device=dev) - col0_loc[blk_of_col]
         v_loc = v_blk[blk_of_col, comp_of_col][:, :crop].contiguous()  # (local columns, t)
         del u_blk, v_blk, yt
@@ -1193,7 +1222,10 @@ def localmd_decomposition(
             else:
                 ps = torch.randn(shape, generator=gen, device=dev, dtype=torch.float32)
             # the prune sketch V Omega (R x t)(t x k'): float32-accurate on the tensor cores (3xTF32) instead of a SIMT GEMM
-            p = compute_lowrank_factorized_svd(su, ops.matmul_3xtf32_any(v_init, ps), only_left=True, factor="chol")
+            sketch = ops.matmul_3xtf32_any(v_init, ps)
+            su.start_host_tables()   # worker thread: U^T U bookkeeping + K7 strip tables, beside the GEMMs just enqueued
+            p = compute_lowrank_factorized_svd(su, sketch, only_left=True, factor="chol")
+            del sketch
         else:
             p = compute_lowrank_factorized_svd(su, v_init, only_left=True, factor="chol")
         say("After performing rank reduction, the updated rank is {}".format(p.shape[1]))

@@ -360,11 +360,20 @@ def block_project(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, w, r, ldo
 
 
 def block_project_tc(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, w, r, ldo=None):
-    """block_project on the tcgen05 tensor cores (3xTF32 with float32 accumulation in tensor memory); rp <= 64."""
+    """block_project on the tcgen05 tensor cores (3xTF32 with float32 accumulation in tensor memory).  The kernels hold at
+    most 64 components per accumulator tile; wider coefficient sets (max_components > 64) go through in slices of 64."""
     _req(movie_t, torch.float32, "movie_t"), _req(w, torch.float32, "w"), _req(starts, torch.int32, "starts")
     nb, bpix, rp = w.shape
-    assert bpix == bh * bw and starts.shape[0] == nb and rp <= 64
+    assert bpix == bh * bw and starts.shape[0] == nb
     ldo = ld if ldo is None else int(ldo)
+    if rp > 64:
+        outs = []
+        for c0 in range(0, r, 64):
+            rc = min(64, r - c0)
+            wc = torch.zeros((nb, bpix, (rc + 3) // 4 * 4), dtype=torch.float32, device=w.device)
+            wc[:, :, :rc] = w[:, :, c0 : c0 + rc]
+            outs.append(block_project_tc(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, wc, rc, ldo))
+        return torch.cat(outs, dim=1)
     out = torch.empty((nb, r, ldo), dtype=torch.float32, device=movie_t.device)
     which = os.environ.get("PMD_BLOCK_PROJECT", "ts")   # development switch between the generations of the kernel
     n_rows = movie_t.numel() // ld
@@ -405,9 +414,17 @@ def block_spatial(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, v, rp):
 
 
 def block_spatial_tc(movie_t, movie_batch_stride, ld, d2, starts, bh, bw, v, rp):
-    """block_spatial on the tcgen05 tensor cores (3xTF32, float32 accumulation in tensor memory); rp <= 64."""
+    """block_spatial on the tcgen05 tensor cores (3xTF32, float32 accumulation in tensor memory); more than 64 components
+    (max_components > 64) go through in slices of 64."""
     _req(movie_t, torch.float32, "movie_t"), _req(v, torch.float32, "v"), _req(starts, torch.int32, "starts")
     nb, r, ldv = v.shape
+    if rp > 64:
+        s_out = torch.zeros((nb, bh * bw, rp), dtype=torch.float32, device=movie_t.device)
+        for c0 in range(0, r, 64):
+            rc = min(64, r - c0)
+            s_out[:, :, c0 : c0 + rc] = block_spatial_tc(movie_t, movie_batch_stride, ld, d2, starts, bh, bw,
+                                                         v[:, c0 : c0 + rc].contiguous(), (rc + 3) // 4 * 4)[:, :, :rc]
+        return s_out
     s_out = torch.empty((nb, bh * bw, rp), dtype=torch.float32, device=movie_t.device)
     if os.environ.get("PMD_BLOCK_SPATIAL", "ts") == "ts":   # development switch between the generations of the kernel
         _call("pmd_block_spatial_ts", _p(movie_t), movie_batch_stride, ld, d2, _p(starts), nb, bh, bw, _p(v.contiguous()), ldv, r, rp,
@@ -551,10 +568,9 @@ def _overlap_pairs(starts, bh, bw):
     return np.stack([b1[order], b2[order]], axis=1).astype(np.int32)
 
 
-def utu_local_csr(starts_host, starts, bh, bw, ranks_host, ranks, col0_host, col0, uvals64):
-    """Canonical CSR (rowptr int64, cols int32, vals float64) of U_loc^T U_loc on the device."""
-    _req(uvals64, torch.float64, "uvals64"), _req(ranks, torch.int32, "ranks"), _req(col0, torch.int64, "col0")
-    dev = uvals64.device
+def utu_host_tables(starts_host, bh, bw, ranks_host):
+    """Host bookkeeping of U_loc^T U_loc: (pairs int32 [n, 2], rowoff int64 [n], rowptr int64 [n_local + 1]) -- pure NumPy,
+    depends on the block grid and the kept ranks only (the driver runs it on its host-table worker thread)."""
     ranks_host = np.asarray(ranks_host, dtype=np.int64)
     pairs = overlap_pairs(starts_host, bh, bw)
     b1, b2 = pairs[:, 0].astype(np.int64), pairs[:, 1].astype(np.int64)
@@ -564,13 +580,22 @@ def utu_local_csr(starts_host, starts, bh, bw, ranks_host, ranks, col0_host, col
     rowoff = ex - ex[first[b1]]
     row_width = np.bincount(b1, weights=r2, minlength=len(ranks_host)).astype(np.int64)
     rowptr = np.concatenate([[0], np.cumsum(np.repeat(row_width, ranks_host))]).astype(np.int64)
+    return pairs, rowoff.astype(np.int64), rowptr
+
+
+def utu_local_csr(starts_host, starts, bh, bw, ranks_host, ranks, col0_host, col0, uvals64, host=None):
+    """Canonical CSR (rowptr int64, cols int32, vals float64) of U_loc^T U_loc on the device.  host: the result of
+    utu_host_tables for the same arguments when it was computed ahead of time."""
+    _req(uvals64, torch.float64, "uvals64"), _req(ranks, torch.int32, "ranks"), _req(col0, torch.int64, "col0")
+    dev = uvals64.device
+    pairs, rowoff, rowptr = host if host is not None else utu_host_tables(starts_host, bh, bw, ranks_host)
     nnz = int(rowptr[-1])
     vals = torch.empty(nnz, dtype=torch.float64, device=dev)
     cols = torch.empty(nnz, dtype=torch.int32, device=dev)
     rowptr_d = torch.from_numpy(rowptr).to(dev)
     if nnz:
         pairs_d = torch.from_numpy(pairs).to(dev)  # named: the tensors must outlive the pointer extraction
-        rowoff_d = torch.from_numpy(rowoff.astype(np.int64)).to(dev)
+        rowoff_d = torch.from_numpy(rowoff).to(dev)
         _call("pmd_utu_pairs", _p(pairs_d), pairs.shape[0], _p(rowoff_d), _p(starts), bh, bw, _p(ranks), _p(col0), _p(uvals64),
               _p(rowptr_d), _p(vals), _p(cols), _stream())
     return rowptr_d, cols, vals

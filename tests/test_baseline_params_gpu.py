@@ -22,7 +22,10 @@ CASES = {
     "c2_20x20": (2048, 128, 128, 20, 1000, 25, (3.0, 5.0)),
     "c3_32x32": (2048, 128, 160, 32, 1000, 25, (3.0, 5.0)),
     "c4_40x40": (1536, 160, 160, 40, 1000, 8, (10.0, 18.0)),
+    # max_components = 80 (> the 64 components of one tensor-core accumulator tile; sketch width 90, Jacobi n = 90)
+    "r80_32x32": (2048, 96, 128, 32, 1000, 20, (3.0, 5.0)),
 }
+RANK = {"r80_32x32": 80}
 _cache = {}
 
 
@@ -31,7 +34,7 @@ def _inputs(name, seed=3):
     movie = make_movie(T, d1, d2, n_cells=n_cells, seed=21, blob_sigma=blob)
     rng = np.random.default_rng(seed)
     nb = len(O.tile_starts(d1, blk)) * len(O.tile_starts(d2, blk))
-    r, K = 50, 15
+    r, K = RANK.get(name, 50), 15
     prune_seed = int(rng.integers(0, 2**31))
     draws = O.Draws(
         bg_frames=rng.choice(T, min(1000, T), replace=False).tolist(),
@@ -63,6 +66,10 @@ def _run(name, pixel_weighting=None):
     return _cache[key]
 
 
+def movie_pixels(name):
+    return CASES[name.split("+")[0]][1] * CASES[name.split("+")[0]][2]
+
+
 def _check(name, arr, det, ref32, ref64):
     rep64 = P.parity_report(arr, det, ref64)
     rep32 = P.parity_report(arr, det, ref32)
@@ -74,6 +81,7 @@ def _check(name, arr, det, ref32, ref64):
     assert rep64["blocks_rank_differ_outside_eps"] == 0, rep64
     assert rep32["blocks_rank_differ_outside_eps"] == 0, rep32
     assert det["ranks"].max() > 4, "the case is meant to exercise multi-slot blocks"
+    assert arr.u.shape[0] == movie_pixels(name)
     if rep64["blocks_rank_differ_within_eps"] == 0:
         assert rep64["csr_indptr_equal"] and rep64["csr_indices_equal"]
         assert P.within_north_star(rep64), rep64

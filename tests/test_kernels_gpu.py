@@ -751,3 +751,4 @@ def test_chol_whiten(ops, n, batch):
     np.testing.assert_allclose(qq, want, atol=5e-5)
     assert np.all(t[-1][:, n - 2] == 0)
     assert np.allclose(np.tril(t[0], -1), 0)
+

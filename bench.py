@@ -326,6 +326,8 @@ def run_ours(args):
         tms = {"__detail__": True}
         localmd_b200.localmd_decomposition(movie, timings=tms, **kw)
         per_step.append(tms)
+        if args.stage_times and rank == 0:
+            sys.stderr.write("step stages: %s\n" % json.dumps({k: round(v, 2) for k, v in tms.items() if isinstance(v, float) and "." not in k}))
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)

@@ -394,6 +394,12 @@ int pmd_utu_pairs(const int32_t* pairs, int64_t n_pairs, const int64_t* pair_row
                   int64_t bh, int64_t bw, const int32_t* ranks, const int64_t* col0, const double* uvals64,
                   const int64_t* rowptr, double* vals, int32_t* cols, void* stream);
 
+/* host-side tables of pmd_utu_pairs (no device work): pair_rowoff [n_pairs] and rowptr [sum(ranks) + 1] from the block
+ * pairs (sorted by b1) and the kept ranks [nb].  Plain C++ so that the Python driver can run it on a worker thread
+ * without holding the interpreter lock. */
+int pmd_utu_host_tables(const int32_t* pairs, int64_t n_pairs, const int64_t* ranks, int64_t nb, int64_t* pair_rowoff,
+                        int64_t* rowptr);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,8 @@
 // block structure is used directly: two local columns interact only when their block windows
 // overlap, so U^T U restricted to the local columns is a block-sparse matrix with one dense
 // rank(b1) x rank(b2) tile per ordered pair of overlapping blocks.  One CTA per pair, float64.
+#include <vector>
+
 #include "common.cuh"
 
 namespace pmd {
@@ -47,4 +49,30 @@ extern "C" int pmd_utu_pairs(const int32_t* pairs, int64_t n_pairs, const int64_
     pmd::utu_pairs_kernel<<<(unsigned)n_pairs, 128, 0, (cudaStream_t)stream>>>(pairs, pair_rowoff, starts, (int)bh, (int)bw, ranks,
                                                                               col0, uvals64, rowptr, vals, cols);
     return pmd::check_launch(fn);
+}
+
+
+// Host bookkeeping of pmd_utu_pairs (plain C++, no device work; the Python driver calls it on its worker thread, where a
+// ctypes call runs without the interpreter lock): for the block pairs sorted by (b1, b2) and the kept ranks,
+//   pair_rowoff[p] = number of entries that precede tile p in each of its rows,  rowptr = CSR row pointer of U_loc^T U_loc.
+extern "C" int pmd_utu_host_tables(const int32_t* pairs, int64_t n_pairs, const int64_t* ranks, int64_t nb, int64_t* pair_rowoff,
+                                   int64_t* rowptr) {
+    const char* fn = "pmd_utu_host_tables";
+    PMD_REQUIRE(pairs && ranks && pair_rowoff && rowptr, fn, "null pointer");
+    PMD_REQUIRE(n_pairs >= 0 && nb > 0, fn, "bad size");
+    std::vector<int64_t> width((size_t)nb, 0);
+    int64_t run = 0, prev = -1;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        const int64_t b1 = pairs[2 * p], b2 = pairs[2 * p + 1];
+        PMD_REQUIRE(b1 >= 0 && b1 < nb && b2 >= 0 && b2 < nb && b1 >= prev, fn, "pairs must be sorted by b1 and index blocks");
+        if (b1 != prev) { run = 0; prev = b1; }
+        pair_rowoff[p] = run;
+        run += ranks[b2];
+        width[(size_t)b1] += ranks[b2];
+    }
+    int64_t row = 0, acc = 0;
+    rowptr[0] = 0;
+    for (int64_t b = 0; b < nb; ++b)
+        for (int64_t c = 0; c < ranks[b]; ++c) { acc += width[(size_t)b]; rowptr[++row] = acc; }
+    return 0;
 }

@@ -463,7 +463,7 @@ class DeviceMovie:
         if self._resident is not None and all(self.lo <= i < self.hi for i in ids):
             if not self._filled:
                 self._fill()
-            return self._resident, torch.as_tensor(ids, dtype=torch.int64, device=self.device) - self.lo
+            return self._resident, ops.h2d(np.asarray(ids, dtype=np.int64) - self.lo, self.device)
         g = self.gather(ids)
         return g, torch.arange(g.shape[0], dtype=torch.int64, device=self.device)
 

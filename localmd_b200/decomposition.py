@@ -530,7 +530,7 @@ class SparseU:
         self.bh, self.bw, self.d1, self.d2 = bh, bw, d1, d2
         self.ranks_host, self.ranks_dev = ranks_host, ranks_dev
         self.col0_host = np.concatenate([[0], np.cumsum(ranks_host)[:-1]]).astype(np.int64)
-        self.col0_dev = torch.from_numpy(self.col0_host).to(ranks_dev.device)
+        self.col0_dev = ops.h2d(self.col0_host, ranks_dev.device)
         self.uvals64, self.uvals32 = uvals64, uvals32
         self.bg = bg  # (K, d) float32
         self.n_local = int(ranks_host.sum())
@@ -612,7 +612,7 @@ class SparseU:
         if st is not None:
             self._ts_host = None
             dev = self.ranks_dev.device
-            self.strips_ts = {k: (torch.from_numpy(v).to(dev) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+            self.strips_ts = {k: (ops.h2d(v, dev) if isinstance(v, np.ndarray) else v) for k, v in st.items()}
             self._ts_inv = None
         if self.strips_ts is not None and (getattr(self, "bimg_ts", None) is None or self._ts_inv is not inv_std):
             self.bimg_ts = ops.pack_strips_ts(self.strips_ts, self.uvals32, self.bg, inv_std, self.bh * self.bw, self.d2)
@@ -1125,9 +1125,9 @@ def localmd_decomposition(
             yt *= pw[row_lo * d2 : row_hi * d2][:, None]
         tm.mark("init_filter")
 
-        starts_dev = torch.from_numpy(starts).to(dev)
+        starts_dev = ops.h2d(starts, dev)
         # block origins relative to the rows of the init movie this rank holds
-        starts_fit = starts_dev if row_lo == 0 else (starts_dev - torch.tensor([row_lo, 0], dtype=torch.int32, device=dev))
+        starts_fit = starts_dev if row_lo == 0 else (starts_dev - ops.h2d(np.array([row_lo, 0], dtype=np.int32), dev))
         block_weights = pyramid_weights(bh, bw)
         # summed pyramid weights of the covering blocks: sum_b shift(block_weights) = Rm^T W Cm with the 0/1
         # incidence matrices of (block-local row, FOV row) and (block-local column, FOV column); exact in float64.
@@ -1139,8 +1139,8 @@ def localmd_decomposition(
         for q in range(bw):
             cm[q, np.asarray(dim_2_iters) + q] = 1.0
         cumw = rm.T @ block_weights.astype(np.float64) @ cm
-        block_weights_dev = torch.from_numpy(block_weights.reshape(-1)).to(dev)
-        cumw_dev = torch.from_numpy(cumw.reshape(-1)).to(dev)
+        block_weights_dev = ops.h2d(block_weights.reshape(-1), dev)
+        cumw_dev = ops.h2d(cumw.reshape(-1), dev)
 
         # ---- block fits (decomposition.py:790-838) -------------------------------------------------
         bs = take("block_sketches")
@@ -1184,7 +1184,7 @@ def localmd_decomposition(
         # ---- weighted sparse assembly (decomposition.py:811-857) -----------------------------------
         # this rank's kept components: weighted values (float64 + float32) and temporal traces
         ranks_loc_host = ranks_host[b0:b1]
-        col0_loc = torch.from_numpy(np.concatenate([[0], np.cumsum(ranks_loc_host)[:-1]]).astype(np.int64)).to(dev)
+        col0_loc = ops.h2d(np.concatenate([[0], np.cumsum(ranks_loc_host)[:-1]]).astype(np.int64), dev)
         ncol_loc = int(ranks_loc_host.sum())
         uv64, uv32 = ops.assemble_u(
             u_blk, bh, bw, starts_dev[b0:b1].contiguous(), ranks_loc, col0_loc, block_weights_dev, cumw_dev, d2, ncol_loc,
@@ -1240,7 +1240,7 @@ def localmd_decomposition(
         # beside the final SVD, whose float64 eigensolver leaves most of the GPU idle.
         main = torch.cuda.current_stream(dev)
         side = _side_stream(dev)
-        row_ids = torch.from_numpy(np.arange(d).reshape((d1, d2), order=order).reshape(-1)).to(dev)
+        row_ids = ops.h2d(np.arange(d).reshape((d1, d2), order=order).reshape(-1), dev)
         csr_out = {}
 
         def start_csr():

@@ -77,6 +77,17 @@ def _tables_tc(device):
     return _table_cache[key]
 
 
+def h2d(a, device, dtype=None):
+    """Host array -> device tensor (small tables).  Deliberately the plain synchronous copy: staging these uploads through
+    page-locked memory with non_blocking copies (so that the host can enqueue further ahead of the device) was measured
+    at C2 and made the job SLOWER whenever stage timings were requested (host stalls of 2-9 ms between consecutive table
+    uploads in the whitening / projection stages, 107 -> 121 ms per job); see DESIGN.md section 5."""
+    t = a if isinstance(a, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    return t.to(device)
+
+
 def movie_dtype_code(t):
     if t.dtype not in PMD_DTYPES:
         raise TypeError("unsupported movie dtype %s" % t.dtype)
@@ -569,18 +580,16 @@ def _overlap_pairs(starts, bh, bw):
 
 
 def utu_host_tables(starts_host, bh, bw, ranks_host):
-    """Host bookkeeping of U_loc^T U_loc: (pairs int32 [n, 2], rowoff int64 [n], rowptr int64 [n_local + 1]) -- pure NumPy,
-    depends on the block grid and the kept ranks only (the driver runs it on its host-table worker thread)."""
-    ranks_host = np.asarray(ranks_host, dtype=np.int64)
+    """Host bookkeeping of U_loc^T U_loc: (pairs int32 [n, 2], rowoff int64 [n], rowptr int64 [n_local + 1]); depends on the
+    block grid and the kept ranks only.  The loops run in the native library (pmd_utu_host_tables: the ctypes call
+    releases the interpreter lock, so the driver's worker thread does not stall the launching thread)."""
+    ranks_host = np.ascontiguousarray(ranks_host, dtype=np.int64)
     pairs = overlap_pairs(starts_host, bh, bw)
-    b1, b2 = pairs[:, 0].astype(np.int64), pairs[:, 1].astype(np.int64)
-    r2 = ranks_host[b2]
-    ex = np.cumsum(r2) - r2                                  # exclusive prefix of tile widths over all pairs
-    first = np.searchsorted(b1, np.arange(len(ranks_host)))  # first pair of every block (pairs sorted by b1)
-    rowoff = ex - ex[first[b1]]
-    row_width = np.bincount(b1, weights=r2, minlength=len(ranks_host)).astype(np.int64)
-    rowptr = np.concatenate([[0], np.cumsum(np.repeat(row_width, ranks_host))]).astype(np.int64)
-    return pairs, rowoff.astype(np.int64), rowptr
+    rowoff = np.empty(pairs.shape[0], dtype=np.int64)
+    rowptr = np.empty(int(ranks_host.sum()) + 1, dtype=np.int64)
+    _lib.check(_lib.lib().pmd_utu_host_tables(_np_ptr(pairs), pairs.shape[0], _np_ptr(ranks_host), len(ranks_host), _np_ptr(rowoff),
+                                              _np_ptr(rowptr)), "pmd_utu_host_tables")
+    return pairs, rowoff, rowptr
 
 
 def utu_local_csr(starts_host, starts, bh, bw, ranks_host, ranks, col0_host, col0, uvals64, host=None):
@@ -592,10 +601,10 @@ def utu_local_csr(starts_host, starts, bh, bw, ranks_host, ranks, col0_host, col
     nnz = int(rowptr[-1])
     vals = torch.empty(nnz, dtype=torch.float64, device=dev)
     cols = torch.empty(nnz, dtype=torch.int32, device=dev)
-    rowptr_d = torch.from_numpy(rowptr).to(dev)
+    rowptr_d = h2d(rowptr, dev)
     if nnz:
-        pairs_d = torch.from_numpy(pairs).to(dev)  # named: the tensors must outlive the pointer extraction
-        rowoff_d = torch.from_numpy(rowoff).to(dev)
+        pairs_d = h2d(pairs, dev)  # named: the tensors must outlive the pointer extraction
+        rowoff_d = h2d(rowoff, dev)
         _call("pmd_utu_pairs", _p(pairs_d), pairs.shape[0], _p(rowoff_d), _p(starts), bh, bw, _p(ranks), _p(col0), _p(uvals64),
               _p(rowptr_d), _p(vals), _p(cols), _stream())
     return rowptr_d, cols, vals

@@ -363,3 +363,22 @@ def test_append_components_and_csr_relabelling_cpu():
     refp.sort_indices()
     np.testing.assert_array_equal(ip.numpy(), refp.indptr)
     np.testing.assert_array_equal(ix.numpy(), refp.indices)
+
+
+def test_utu_host_tables_match_numpy_formulation():
+    """pmd_utu_host_tables (native host routine, no device work) against the NumPy statement of the same bookkeeping:
+    row offsets of every block-pair tile and the CSR row pointer of U_loc^T U_loc."""
+    from localmd_b200 import ops
+
+    rng = np.random.default_rng(0)
+    rows, cols = list(range(0, 100, 10)), list(range(0, 90, 10))
+    starts = np.stack(np.meshgrid(rows, cols, indexing="ij"), -1).reshape(-1, 2)
+    ranks = rng.integers(0, 6, len(starts)).astype(np.int64)
+    pairs, rowoff, rowptr = ops.utu_host_tables(starts, 20, 20, ranks)
+    b1, b2 = pairs[:, 0].astype(np.int64), pairs[:, 1].astype(np.int64)
+    r2 = ranks[b2]
+    ex = np.cumsum(r2) - r2
+    first = np.searchsorted(b1, np.arange(len(ranks)))
+    np.testing.assert_array_equal(rowoff, ex - ex[first[b1]])
+    width = np.bincount(b1, weights=r2, minlength=len(ranks)).astype(np.int64)
+    np.testing.assert_array_equal(rowptr, np.concatenate([[0], np.cumsum(np.repeat(width, ranks))]))

@@ -26,51 +26,66 @@ __device__ __forceinline__ void cp_async_wait() {
 // ------------------------------------------------------------------------------------------------
 // yT[p][i] = (movie[frames[i]][p] - mean[p]) / stdv[p]     (32 x 32 transposing tiles)
 // ------------------------------------------------------------------------------------------------
-// A CTA transposes kSTTileSets = 4 neighbouring 32 x 32 tiles: a warp reads 4 x 128 contiguous bytes of the same frame back
-// to back (DRAM sees 512-byte bursts instead of isolated 128-byte lines) and has 16 independent loads in flight.
+// A CTA transposes a [128 frames x 128 pixels] tile (kSTTileSets = 4 neighbouring 32-pixel column sets x kSTFrameSets = 4
+// sets of 32 frames): a warp reads 4 x 128 contiguous bytes of the same frame back to back and writes 4 x 128 contiguous
+// bytes of the same pixel row back to back, so DRAM sees 512-byte bursts on both sides instead of isolated 128-byte lines
+// (the pixel rows of the output are ld * 4 bytes apart); 16 independent loads in flight per thread.
 constexpr int kSTTileSets = 4;
+constexpr int kSTFrameSets = 4;
 
 template <typename T>
 __global__ void __launch_bounds__(256)
 standardize_frames_t_kernel(const T* __restrict__ movie, int64_t d, const int64_t* __restrict__ frames, int64_t n,
                             const float* __restrict__ mean, const float* __restrict__ stdv, float* __restrict__ out,
                             int64_t ld) {
-    __shared__ float tile[kSTTileSets][32][33];
+    extern __shared__ float st_tile[];   // [kSTTileSets][32 * kSTFrameSets][33]
+    auto tile = [&](int s, int f, int p) -> float& { return st_tile[(s * (32 * kSTFrameSets) + f) * 33 + p]; };
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int64_t p0 = (int64_t)blockIdx.x * (32 * kSTTileSets), i0 = (int64_t)blockIdx.y * 32;
-    int64_t fr[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int64_t i = i0 + ty + 8 * j;
-        fr[j] = i < n ? frames[i] : -1;
-    }
-    float raw[kSTTileSets][4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {      // the 4 lines of one frame are requested back to back
-#pragma unroll
-        for (int s = 0; s < kSTTileSets; ++s) {
-            const int64_t p = p0 + 32 * s + tx;
-            raw[s][j] = (fr[j] >= 0 && p < d) ? to_f32(movie[fr[j] * d + p]) : 0.f;
-        }
-    }
+    const int64_t p0 = (int64_t)blockIdx.x * (32 * kSTTileSets), i0 = (int64_t)blockIdx.y * (32 * kSTFrameSets);
+    float mu[kSTTileSets], sd[kSTTileSets];
 #pragma unroll
     for (int s = 0; s < kSTTileSets; ++s) {
         const int64_t p = p0 + 32 * s + tx;
-        float mu = 0.f, sd = 1.f;
-        if (p < d) {
-            mu = mean[p];
-            sd = stdv[p];
+        mu[s] = p < d ? mean[p] : 0.f;
+        sd[s] = p < d ? stdv[p] : 1.f;
+    }
+#pragma unroll 1
+    for (int fs = 0; fs < kSTFrameSets; ++fs) {
+        int64_t fr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int64_t i = i0 + 32 * fs + ty + 8 * j;
+            fr[j] = i < n ? frames[i] : -1;
+        }
+        float raw[kSTTileSets][4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {      // the 4 lines of one frame are requested back to back
+#pragma unroll
+            for (int s = 0; s < kSTTileSets; ++s) {
+                const int64_t p = p0 + 32 * s + tx;
+                raw[s][j] = (fr[j] >= 0 && p < d) ? to_f32(movie[fr[j] * d + p]) : 0.f;
+            }
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tile[s][ty + 8 * j][tx] = (fr[j] >= 0 && p < d) ? (raw[s][j] - mu) / sd : 0.f;
+        for (int s = 0; s < kSTTileSets; ++s) {
+            const int64_t p = p0 + 32 * s + tx;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                tile(s, 32 * fs + ty + 8 * j, tx) = (fr[j] >= 0 && p < d) ? (raw[s][j] - mu[s]) / sd[s] : 0.f;
+        }
     }
     __syncthreads();
 #pragma unroll
     for (int s = 0; s < kSTTileSets; ++s) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int64_t pp = p0 + 32 * s + ty + 8 * j, i = i0 + tx;
-            if (pp < d && i < ld) out[pp * ld + i] = tile[s][tx][ty + 8 * j];
+            const int64_t pp = p0 + 32 * s + ty + 8 * j;
+            if (pp >= d) continue;
+#pragma unroll
+            for (int fs = 0; fs < kSTFrameSets; ++fs) {   // the 4 lines of one pixel row are written back to back
+                const int64_t i = i0 + 32 * fs + tx;
+                if (i < ld) out[pp * ld + i] = tile(s, 32 * fs + tx, ty + 8 * j);
+            }
         }
     }
 }
@@ -137,6 +152,40 @@ block_pool_full_kernel(const float* __restrict__ yT, int64_t ld, int64_t t, int6
             v = sum / (float)((r1 - r0) * (c1 - c0));
         }
         out[(int64_t)p * ld] = v;
+    }
+}
+
+// the same with 4 consecutive frames per thread (16-byte loads / stores: 512-byte requests per warp); identical arithmetic
+__global__ void __launch_bounds__(256)
+block_pool_full4_kernel(const float* __restrict__ yT, int64_t ld, int64_t t, int64_t d2, const int32_t* __restrict__ starts,
+                        int bh, int bw, int saf, float* __restrict__ pooled) {
+    const int ph = (bh + saf - 1) / saf, pw = (bw + saf - 1) / saf;
+    const int lo_h = (ph * saf - bh) / 2, lo_w = (pw * saf - bw) / 2;
+    const int P = ph * pw;
+    const int64_t b = blockIdx.y;
+    const int i0 = starts[2 * b], j0 = starts[2 * b + 1];
+    const int64_t f = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (f >= ld) return;
+    const float* base = yT + ((int64_t)i0 * d2 + j0) * ld + f;
+    float* out = pooled + b * P * ld + f;
+#pragma unroll 2
+    for (int p = 0; p < P; ++p) {
+        const int pi = p / pw, pj = p - pi * pw;
+        const int r0 = max(pi * saf - lo_h, 0), r1 = min(pi * saf - lo_h + saf, bh);
+        const int c0 = max(pj * saf - lo_w, 0), c1 = min(pj * saf - lo_w + saf, bw);
+        float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int r = r0; r < r1; ++r)
+            for (int c = c0; c < c1; ++c) {
+                const float4 y = __ldg(reinterpret_cast<const float4*>(base + ((int64_t)r * d2 + c) * ld));
+                sum.x += y.x; sum.y += y.y; sum.z += y.z; sum.w += y.w;
+            }
+        const float cnt = (float)((r1 - r0) * (c1 - c0));
+        float4 v;
+        v.x = f + 0 < t ? sum.x / cnt : 0.f;
+        v.y = f + 1 < t ? sum.y / cnt : 0.f;
+        v.z = f + 2 < t ? sum.z / cnt : 0.f;
+        v.w = f + 3 < t ? sum.w / cnt : 0.f;
+        *reinterpret_cast<float4*>(out + (int64_t)p * ld) = v;
     }
 }
 
@@ -379,13 +428,16 @@ extern "C" int pmd_standardize_frames_t(const void* movie, int dtype, int64_t d,
     const char* fn = "pmd_standardize_frames_t";
     PMD_REQUIRE(movie && frames && mean && stdv && out, fn, "null pointer");
     PMD_REQUIRE(d > 0 && n_frames > 0 && ld >= n_frames, fn, "bad size");
-    const int64_t gy = (ld + 31) / 32;
-    PMD_REQUIRE(gy <= 65535, fn, "more than 65535*32 frames per call");
+    const int64_t gy = (ld + 32 * pmd::kSTFrameSets - 1) / (32 * pmd::kSTFrameSets);
+    PMD_REQUIRE(gy <= 65535, fn, "more than 65535*128 frames per call");
     dim3 grid((unsigned)((d + 32 * pmd::kSTTileSets - 1) / (32 * pmd::kSTTileSets)), (unsigned)gy);
     cudaStream_t st = (cudaStream_t)stream;
+    const int smem = pmd::kSTTileSets * 32 * pmd::kSTFrameSets * 33 * (int)sizeof(float);
     PMD_DISPATCH_DTYPE(dtype, fn, {
-        pmd::standardize_frames_t_kernel<scalar_t><<<grid, 256, 0, st>>>((const scalar_t*)movie, d, frames, n_frames, mean, stdv,
-                                                                         out, ld);
+        cudaError_t e = cudaFuncSetAttribute(pmd::standardize_frames_t_kernel<scalar_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e)); return (int)e; }
+        pmd::standardize_frames_t_kernel<scalar_t><<<grid, 256, smem, st>>>((const scalar_t*)movie, d, frames, n_frames, mean, stdv,
+                                                                            out, ld);
     });
     return pmd::check_launch(fn);
 }
@@ -411,8 +463,13 @@ extern "C" int pmd_block_pool_full(const float* yt, int64_t ld, int64_t t, int64
     const int64_t P = ((bh + saf - 1) / saf) * ((bw + saf - 1) / saf);
     const int64_t tp = t / taf;
     cudaStream_t st = (cudaStream_t)stream;
-    dim3 grid((unsigned)((ld + 255) / 256), (unsigned)nb);
-    pmd::block_pool_full_kernel<<<grid, 256, 0, st>>>(yt, ld, t, d2, starts, (int)bh, (int)bw, (int)saf, pooled);
+    if (ld % 4 == 0 && ((uintptr_t)yt % 16) == 0 && ((uintptr_t)pooled % 16) == 0) {
+        dim3 grid((unsigned)((ld / 4 + 255) / 256), (unsigned)nb);
+        pmd::block_pool_full4_kernel<<<grid, 256, 0, st>>>(yt, ld, t, d2, starts, (int)bh, (int)bw, (int)saf, pooled);
+    } else {
+        dim3 grid((unsigned)((ld + 255) / 256), (unsigned)nb);
+        pmd::block_pool_full_kernel<<<grid, 256, 0, st>>>(yt, ld, t, d2, starts, (int)bh, (int)bw, (int)saf, pooled);
+    }
     const int64_t total = nb * P * tp;
     pmd::block_tavg_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(pooled, ld, nb * P, tp, (int)taf, bta);
     return pmd::check_launch(fn);

@@ -12,6 +12,7 @@ Same signature, defaults, guards and result object as the reference.  Extra keyw
 README aliases block_height/block_width/frames_to_init are accepted.
 """
 import concurrent.futures
+import contextlib
 import datetime
 import math
 import os
@@ -103,6 +104,20 @@ def identify_window_chunks(frame_range, total_frames, window_chunks, rng, starti
 _ACTIVE_TIMER = None
 _SIDE_STREAMS = {}
 _HOST_POOL = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="pmd-host-tables")
+
+
+@contextlib.contextmanager
+def _short_switch_interval(seconds=1e-4):
+    """The launching thread and the host-table worker thread hand the interpreter lock back and forth (every ctypes call
+    into the library releases it).  With CPython's default 5 ms switch interval the thread that wants the lock back can
+    wait that long while the other runs Python code: measured as occasional 5-7 ms holes in the device queue where the
+    driver waits for the worker's tables (whitening, projection).  The interval is restored on exit."""
+    old = sys.getswitchinterval()
+    sys.setswitchinterval(seconds)
+    try:
+        yield
+    finally:
+        sys.setswitchinterval(old)
 
 
 def _side_stream(dev, priority=0):
@@ -965,7 +980,7 @@ def localmd_decomposition(
     draws = draws if draws is not None else object()
     take = lambda name: getattr(draws, name, None)  # noqa: E731
 
-    with torch.cuda.device(dev), ops.fp32_matmul():
+    with torch.cuda.device(dev), ops.fp32_matmul(), _short_switch_interval():
         global _ACTIVE_TIMER
         tm = _Timer(timings, dev)
         _ACTIVE_TIMER = tm

@@ -400,6 +400,15 @@ int pmd_utu_pairs(const int32_t* pairs, int64_t n_pairs, const int64_t* pair_row
 int pmd_utu_host_tables(const int32_t* pairs, int64_t n_pairs, const int64_t* ranks, int64_t nb, int64_t* pair_rowoff,
                         int64_t* rowptr);
 
+/* Operand preparation of the float32-accurate tensor-core GEMMs of the mixing step (pmd_loader.py:411-412,
+ * dense @ (sparse @ Yc); decomposition.py:1090-1099 back-multiplications):  a b ~= a_hi b_hi (TF32 GEMM) +
+ * [a_lo | a_hi][b_hi ; b_lo] (one bf16 GEMM of twice the depth).  In one pass x [rows][ldx] is overwritten by its TF32-exact
+ * part hi and the bf16 image `pair` is written:
+ *   mode 0 (right operand, depth = rows): pair [2 rows][ldp]:  pair[r][c] = bf16(hi), pair[rows + r][c] = bf16(lo)
+ *   mode 1 (left operand,  depth = cols): pair [rows][ldp >= 2 cols]:  pair[r][c] = bf16(lo), pair[r][cols + c] = bf16(hi)
+ * cols, ldx, ldp multiples of 4. */
+int pmd_split_tf32_bf16(float* x, int64_t rows, int64_t cols, int64_t ldx, void* pair, int64_t ldp, int mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1308,16 +1308,20 @@ def project_movie(movie: DeviceMovie, su: SparseU, p, mean, inv_std):
     rpad = (su.n_cols + 7) // 8 * 8
     pt = torch.zeros((k, rpad), dtype=torch.float32, device=dev)
     pt[:, : su.n_cols] = p.t()
+    # mixing GEMM P^T Z at float32 accuracy as ONE TF32 + ONE bf16 library GEMM (ops.matmul_split): operands split once
+    pt_pair = ops.split_pairs(pt, 1)
     for f0, chunk in movie.batches():
         n = chunk.shape[0]
-        npad = (n + 3) // 4 * 4
+        npad = (n + 7) // 8 * 8
         z = torch.empty((rpad, npad), dtype=torch.float32, device=dev)
         z[su.n_cols :].zero_()
         if npad != n:
             z[:, n:].zero_()
         su.project(chunk, mean, inv_std, z[: su.n_cols])
         _submark("projection.dense")
-        v_full[:, f0 : f0 + n].copy_(ops.matmul_3xtf32(pt, z)[:, :n])
+        z_pair = ops.split_pairs(z, 0)
+        v_full[:, f0 : f0 + n].copy_(ops.matmul_split(pt, pt_pair, z, z_pair)[:, :n])
+        del z_pair
         _submark("projection.mix")
         del z
     return v_full

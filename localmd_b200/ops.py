@@ -284,24 +284,48 @@ def matmul_3xtf32(a, b):
     return out
 
 
+def split_pairs(x, mode):
+    """In place x <- hi(x) (TF32-exact part); returns the bf16 correction operand: mode 0 (x is the right operand, (K, n)) ->
+    (2K, n) = [bf16(hi); bf16(lo)], mode 1 (x is the left operand, (m, K)) -> (m, 2K) = [bf16(lo) | bf16(hi)]."""
+    _req(x, torch.float32, "x")
+    rows, cols = x.shape
+    pair = torch.empty((2 * rows, cols) if mode == 0 else (rows, 2 * cols), dtype=torch.bfloat16, device=x.device)
+    _call("pmd_split_tf32_bf16", _p(x), rows, cols, cols, _p(pair), pair.shape[1], int(mode), _stream())
+    return pair
+
+
+def matmul_split(a_hi, a_pair, b_hi, b_pair):
+    """a @ b at float32 accuracy from operands prepared by split_pairs: one TF32 library GEMM (exact products of the hi
+    parts) + one bf16 library GEMM of twice the depth carrying a_lo b_hi + a_hi b_lo (dropped terms < 2^-18 relative)."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        out = torch.mm(a_pair, b_pair, out_dtype=torch.float32)
+        out.addmm_(a_hi, b_hi)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    return out
+
+
 def matmul_3xtf32_any(a, b):
-    """matmul_3xtf32 for arbitrary shapes: every dimension is zero padded to a multiple of 8 (the TF32 tensor-core
-    kernels want 16-byte aligned rows), the result is sliced back."""
+    """float32-accurate a @ b on the tensor cores for arbitrary shapes: every dimension is zero padded to a multiple of 8
+    (the tensor-core kernels want 16-byte aligned rows) into fresh copies, which are split in place (split_pairs) and
+    multiplied by matmul_split (one TF32 + one bf16 library GEMM); the result is sliced back."""
     m, k = a.shape
     k2, n = b.shape
     assert k == k2
     mp, kp, np_ = (m + 7) // 8 * 8, (k + 7) // 8 * 8, (n + 7) // 8 * 8
-    if (mp, kp) != (m, k):
+    if (mp, kp) != (m, k) or not a.is_contiguous():
         ap = torch.zeros((mp, kp), dtype=torch.float32, device=a.device)
         ap[:m, :k] = a
     else:
-        ap = a
-    if (kp, np_) != (k, n):
+        ap = a.clone()
+    if (kp, np_) != (k, n) or not b.is_contiguous():
         bp = torch.zeros((kp, np_), dtype=torch.float32, device=b.device)
         bp[:k, :n] = b
     else:
-        bp = b
-    return matmul_3xtf32(ap, bp)[:m, :n]
+        bp = b.clone()
+    return matmul_split(ap, split_pairs(ap, 1), bp, split_pairs(bp, 0))[:m, :n]
 
 
 def block_orth_fits(m, n):

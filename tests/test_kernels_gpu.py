@@ -150,6 +150,28 @@ def test_matmul_3xtf32(ops):
     assert np.max(np.abs(got - ref) / scale) < 2e-6  # float32-class accuracy (plain TF32 would be ~1e-3)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,k,n", [(300, 1000, 700), (50, 37, 101), (1650, 808, 512)])
+def test_matmul_split_tf32_bf16_pairs(ops, m, k, n):
+    """One TF32 + one bf16 GEMM on operands split by pmd_split_tf32_bf16: float32-class accuracy, and the split itself:
+    x = hi + lo exactly, hi representable in TF32."""
+    rng = np.random.default_rng(m + n)
+    a = (rng.standard_normal((m, k)) * np.exp(rng.uniform(-8, 8, (m, 1)))).astype(np.float32)
+    b = (rng.standard_normal((k, n)) * np.exp(rng.uniform(-8, 8, (1, n)))).astype(np.float32)
+    got = ops.matmul_3xtf32_any(dev(a), dev(b)).cpu().numpy().astype(np.float64)
+    ref = a.astype(np.float64) @ b.astype(np.float64)
+    scale = np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64)
+    assert np.max(np.abs(got - ref) / scale) < 4e-6  # float32-class accuracy (plain TF32 would be ~1e-3)
+    if k % 4 == 0 and n % 4 == 0:
+        x = dev(b)
+        pair = ops.split_pairs(x, 0).float().cpu().numpy()
+        hi = x.cpu().numpy()
+        assert np.all((hi.view(np.uint32) & 0x1FFF) == 0)
+        np.testing.assert_allclose(pair[:k], hi, rtol=2.0**-8)
+        np.testing.assert_allclose(pair[k:], b - hi, rtol=2.0**-8, atol=1e-38)
+        assert np.max(np.abs(b - hi) / np.maximum(np.abs(b), 1e-30)) <= 2.0**-11
+
+
 @pytest.mark.parametrize("m,n,ld,rank", [(100, 60, 60, 60), (400, 50, 52, 50), (400, 50, 52, 17), (144, 11, 11, 11), (30, 8, 12, 5)])
 def test_block_orth(ops, m, n, ld, rank):
     """Fused CholQR2: orthonormal columns spanning the input's column space; dependent columns dropped."""

@@ -803,6 +803,24 @@ class SparseU:
         ops.project_dense(movie2d, self.bg, mean, inv_std, zb)
 
 
+def _sym_product_f64(a, b=None):
+    """a @ b (default b = a^T) for a product known to be SYMMETRIC, float64: only the blocks on and above the diagonal of
+    a 2 x 2 partition are computed by the library GEMM (3/4 of the flops: 2.6 instead of 3.3 ms for the 1650 x 20000 Gram
+    of the final SVD, bit-identical blocks), the lower block is the transpose of the upper one."""
+    n = a.shape[0]
+    if n < 256:
+        return torch.matmul(a, a.t() if b is None else b)
+    h = (n // 2 + 7) // 8 * 8
+    bt = a.t() if b is None else b
+    g = torch.empty((n, n), dtype=a.dtype, device=a.device)
+    g[:h, :h] = torch.matmul(a[:h], bt[:, :h])
+    g[h:, h:] = torch.matmul(a[h:], bt[:, h:])
+    off = torch.matmul(a[:h], bt[:, h:])
+    g[:h, h:] = off
+    g[h:, :h] = off.t()
+    return g
+
+
 def compute_lowrank_factorized_svd(u, v, only_left=False, factor="eigh"):
     """decomposition.py:936-1010 on the GPU.  `u` is a SparseU (or a scipy sparse matrix, converted),
     `v` a dense (R, t') tensor/array.  Returns the spatial mixing matrix P (R, k) (device tensor) such
@@ -820,7 +838,7 @@ def compute_lowrank_factorized_svd(u, v, only_left=False, factor="eigh"):
     right = v.to(torch.float64) if R > v.shape[1] else torch.eye(R, dtype=torch.float64, device=dev)
     z = u.utu_times_f64(right)  # (R, m) float64
     _submark("whiten.utu")
-    g = torch.matmul(right.t(), z)
+    g = _sym_product_f64(right.t(), z)
     g = 0.5 * (g + g.t())
     _submark("whiten.gram")
     mix64 = None
@@ -830,7 +848,7 @@ def compute_lowrank_factorized_svd(u, v, only_left=False, factor="eigh"):
         ok = (info == 0) & (dg.min() > 1e-6 * dg.max())  # cond(G) < ~1e12 : safe in float64
         # the triangular solve is enqueued before the verdict is read back (the read is a host synchronisation; the device
         # keeps working through it) and discarded in the rare singular case
-        spec = torch.linalg.solve_triangular(chol, right.t(), upper=False).t()
+        spec = torch.linalg.solve_triangular(chol.t(), right, upper=True, left=False)   # X L^T = M (2.0 ms; L X^T = M^T: 2.7 ms)
         if bool(ok.item()):
             mix64 = spec
             _submark("whiten.chol")
@@ -879,9 +897,7 @@ def projected_svd(projection, data, group=None, after_gram=None):
         dist.all_reduce(nt, group=group)
         n_total = int(nt.item())
     if k <= n_total:
-        d64 = data.to(torch.float64)
-        gram = torch.matmul(d64, d64.t())
-        del d64
+        gram = _sym_product_f64(data.to(torch.float64))
         if group is not None:
             dist.all_reduce(gram, group=group)
         gram = 0.5 * (gram + gram.t())

@@ -409,6 +409,20 @@ int pmd_utu_host_tables(const int32_t* pairs, int64_t n_pairs, const int64_t* ra
  * cols, ldx, ldp multiples of 4. */
 int pmd_split_tf32_bf16(float* x, int64_t rows, int64_t cols, int64_t ldx, void* pair, int64_t ldp, int mode, void* stream);
 
+/* Large SYMMETRIC float64 product on the FP64 tensor cores (mma.sync m8n8k4):  C[i][j] = sum_k A(i, k) B(j, k), n x n,
+ * for a product the caller knows to be symmetric (b == NULL: B = A, the Gram A A^T).  Only the 128 x 128 tiles on and
+ * above the diagonal are computed; both triangles of C are written from them, so C is exactly symmetric.
+ *   layout 0: A(i, k) = a[i * lda + k], B(j, k) = b[j * ldb + k]   (rows with the inner dimension contiguous)
+ *   layout 1: A(i, k) = a[k * lda + i], B(j, k) = b[k * ldb + j]   (C = A^T B for row-major [k_len][n] operands)
+ * a_dtype / b_dtype: PMD_F32 or PMD_F64 (float32 operands are converted while they are staged: exact).  Supported:
+ * layout 0 f32/f32 and f64/f64, layout 1 f32/f64 and f64/f64.  The inner dimension is cut into `splits` chunks (1..64)
+ * whose partial tiles go to `work` (splits * nt (nt + 1) / 2 * 128 * 128 doubles, nt = ceil(n / 128)) and are added in
+ * ascending order (deterministic).
+ * replaces: the Gram of fewer_rows_svd_routine (decomposition.py:1063-1071) and M^T (U^T U M) of
+ *           compute_lowrank_factorized_svd (decomposition.py:974-983). */
+int pmd_sym_product_f64(const void* a, int a_dtype, int64_t lda, const void* b, int b_dtype, int64_t ldb, int layout,
+                        int64_t n, int64_t k_len, int64_t splits, double* work, double* c, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

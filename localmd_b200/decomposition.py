@@ -803,24 +803,6 @@ class SparseU:
         ops.project_dense(movie2d, self.bg, mean, inv_std, zb)
 
 
-def _sym_product_f64(a, b=None):
-    """a @ b (default b = a^T) for a product known to be SYMMETRIC, float64: only the blocks on and above the diagonal of
-    a 2 x 2 partition are computed by the library GEMM (3/4 of the flops: 2.6 instead of 3.3 ms for the 1650 x 20000 Gram
-    of the final SVD, bit-identical blocks), the lower block is the transpose of the upper one."""
-    n = a.shape[0]
-    if n < 256:
-        return torch.matmul(a, a.t() if b is None else b)
-    h = (n // 2 + 7) // 8 * 8
-    bt = a.t() if b is None else b
-    g = torch.empty((n, n), dtype=a.dtype, device=a.device)
-    g[:h, :h] = torch.matmul(a[:h], bt[:, :h])
-    g[h:, h:] = torch.matmul(a[h:], bt[:, h:])
-    off = torch.matmul(a[:h], bt[:, h:])
-    g[:h, h:] = off
-    g[h:, :h] = off.t()
-    return g
-
-
 def compute_lowrank_factorized_svd(u, v, only_left=False, factor="eigh"):
     """decomposition.py:936-1010 on the GPU.  `u` is a SparseU (or a scipy sparse matrix, converted),
     `v` a dense (R, t') tensor/array.  Returns the spatial mixing matrix P (R, k) (device tensor) such
@@ -838,8 +820,8 @@ def compute_lowrank_factorized_svd(u, v, only_left=False, factor="eigh"):
     right = v.to(torch.float64) if R > v.shape[1] else torch.eye(R, dtype=torch.float64, device=dev)
     z = u.utu_times_f64(right)  # (R, m) float64
     _submark("whiten.utu")
-    g = _sym_product_f64(right.t(), z)
-    g = 0.5 * (g + g.t())
+    # G = M^T (U^T U M): own FP64 tensor-core kernel, upper tiles only, mirrored (exactly symmetric)
+    g = ops.sym_product_f64(right, z, layout=1)
     _submark("whiten.gram")
     mix64 = None
     if factor == "chol" and only_left:
@@ -897,10 +879,11 @@ def projected_svd(projection, data, group=None, after_gram=None):
         dist.all_reduce(nt, group=group)
         n_total = int(nt.item())
     if k <= n_total:
-        gram = _sym_product_f64(data.to(torch.float64))
+        # float64 Gram of the float32 rows on the FP64 tensor cores (own kernel: operands converted while they are staged,
+        # tiles on and above the diagonal only, both triangles written from them -> exactly symmetric)
+        gram = ops.sym_product_f64(data if data.stride(1) == 1 else data.contiguous())
         if group is not None:
             dist.all_reduce(gram, group=group)
-        gram = 0.5 * (gram + gram.t())
         _submark("final_svd.gram")
         if after_gram is not None:
             after_gram()

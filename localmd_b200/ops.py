@@ -25,7 +25,7 @@ NUMPY_NATIVE = {np.dtype(k): v for k, v in [("float32", torch.float32), ("uint16
                                                ("uint8", torch.uint8), ("float64", torch.float64), ("int32", torch.int32)]}
 
 LAUNCHES = {"count": 0, "by_name": {}}  # number of libpmd kernel launches issued (bench.py reports it)
-_KERNELS_PER_CALL = {"pmd_block_stats_rank": 3, "pmd_block_pool_full": 2}
+_KERNELS_PER_CALL = {"pmd_block_stats_rank": 3, "pmd_block_pool_full": 2, "pmd_sym_product_f64": 2}
 
 
 def _count(name, n=None):
@@ -138,6 +138,51 @@ def gram_f64(a, batch, n, m_len, batch_stride, row_stride, inner_stride):
         m = min(step, batch - s)
         _call("pmd_gram_f64", ctypes.c_void_p(a.data_ptr() + 4 * s * batch_stride), m, n, m_len, batch_stride, row_stride,
               inner_stride, _p(c[s:]), _stream())
+    return c
+
+
+
+_SYM_TILE = 128
+_sym_work = {}
+
+
+def sym_splits(n, k_len, sms=148):
+    """Number of inner-dimension chunks of pmd_sym_product_f64: the split whose nt (nt + 1) / 2 * splits units fill whole
+    waves of the SMs best (one 128 x 128 unit per SM at a time), chunks of at least 256 values, fewest chunks on ties."""
+    nt = -(-n // _SYM_TILE)
+    tiles = nt * (nt + 1) // 2
+    best, best_eff = 1, 0.0
+    for s in range(1, 65):
+        if s > 1 and k_len // s < 256:
+            break
+        units = tiles * s
+        eff = units / (sms * -(-units // sms))
+        if eff > best_eff + 1e-9:
+            best, best_eff = s, eff
+    return best
+
+
+def sym_product_f64(a, b=None, layout=0):
+    """float64 product known to be SYMMETRIC, on the FP64 tensor cores (csrc/sym_f64.cu; see header):
+    layout 0: a (n, k) [, b (n, k)] -> a b^T (b None: the Gram a a^T);  layout 1: a (k, n), b (k, n) -> a^T b.
+    Operands float32 or float64 (layout 0: both the same type; layout 1: b float64), rows contiguous."""
+    if a.dim() != 2 or a.stride(1) != 1 or not a.is_cuda:
+        raise ValueError("a must be a 2-D CUDA tensor with contiguous rows (there is no CPU fallback)")
+    if b is not None and (b.dim() != 2 or b.stride(1) != 1 or b.shape != a.shape or b.device != a.device):
+        raise ValueError("b must match a")
+    if a.dtype not in (torch.float32, torch.float64) or (b is not None and b.dtype not in (torch.float32, torch.float64)):
+        raise TypeError("operands must be float32 or float64")
+    n, k_len = (a.shape[0], a.shape[1]) if layout == 0 else (a.shape[1], a.shape[0])
+    splits = sym_splits(n, k_len)
+    nt = -(-n // _SYM_TILE)
+    need = splits * (nt * (nt + 1) // 2) * _SYM_TILE * _SYM_TILE
+    key = (str(a.device), torch.cuda.current_stream().cuda_stream)
+    work = _sym_work.get(key)
+    if work is None or work.numel() < need:
+        work = _sym_work[key] = torch.empty(need, dtype=torch.float64, device=a.device)
+    c = torch.empty((n, n), dtype=torch.float64, device=a.device)
+    _call("pmd_sym_product_f64", _p(a), PMD_DTYPES[a.dtype], a.stride(0), _p(b), PMD_DTYPES[b.dtype] if b is not None else 0,
+          b.stride(0) if b is not None else 0, int(layout), n, k_len, splits, _p(work), _p(c), _stream())
     return c
 
 

@@ -774,3 +774,26 @@ def test_chol_whiten(ops, n, batch):
     assert np.all(t[-1][:, n - 2] == 0)
     assert np.allclose(np.tril(t[0], -1), 0)
 
+
+
+# ------------------------------------------------------------------------------------------------ symmetric float64 products
+@pytest.mark.parametrize("n,k,layout,dt", [(37, 50, 0, np.float32), (130, 1000, 0, np.float32), (300, 2500, 0, np.float64),
+                                           (257, 777, 1, np.float32), (129, 4099, 1, np.float64), (1, 3, 0, np.float32)])
+def test_sym_product_f64(ops, n, k, layout, dt):
+    """pmd_sym_product_f64 against NumPy float64: Gram a a^T (layout 0) and a^T (S a) with S symmetric (layout 1)."""
+    rng = np.random.default_rng(n + k)
+    if layout == 0:
+        a = rng.standard_normal((n, k)).astype(dt)
+        got = ops.sym_product_f64(dev(a)).cpu().numpy()
+        want = a.astype(np.float64) @ a.astype(np.float64).T
+    else:
+        a = rng.standard_normal((k, n)).astype(dt)
+        s = rng.standard_normal((k, k))
+        b = (s + s.T) @ a.astype(np.float64)
+        got = ops.sym_product_f64(dev(a), dev(b), layout=1).cpu().numpy()
+        want = a.astype(np.float64).T @ b
+    assert np.array_equal(got, got.T)                                   # both triangles from the same tiles
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.abs(want).max())   # float64 accumulation, reordered sums
+    if layout == 0:
+        again = ops.sym_product_f64(dev(a)).cpu().numpy()
+        assert np.array_equal(got, again)                               # deterministic

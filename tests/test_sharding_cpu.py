@@ -124,7 +124,13 @@ def test_exchange_frame_rows_gloo():
 
 
 def _svd(rank, world):
+    from localmd_b200 import ops
     from localmd_b200.decomposition import projected_svd
+
+    # the product has no CPU path: this test covers the COLLECTIVE logic of the frame-sharded final SVD (Gram all-reduce,
+    # local Vt block), so the two device products are replaced by plain torch stand-ins for the duration of the test
+    ops.sym_product_f64 = lambda a, b=None, layout=0: a.double() @ a.double().t()
+    ops.matmul_3xtf32_any = lambda a, b: a @ b
 
     rng = np.random.default_rng(3)
     k, T, R = 130, 3000, 150

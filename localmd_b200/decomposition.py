@@ -424,11 +424,17 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
     _submark("blocks.jacobi2")
     lpad = torch.zeros((nb, rp, rp), dtype=torch.float32, device=dev)
     lpad[:, :r, :r] = lmat
-    # rotation into the singular vectors (decomposition.py:319-323): library SIMT batched GEMMs, pinned to full float32 (a
-    # hand-written packed-FMA kernel measured 2.8 ms against the library's 2.3 ms at C2 and was dropped)
+    # rotation into the singular vectors (decomposition.py:319-323).  V <- L^T V runs on the tensor cores through the block
+    # projection kernel: V[b] (r rows of ld frames) is a 1 x r "pixel block" of a pixel-major movie and L[b] its coefficient
+    # images (1.16 ms against 2.25 ms for the library's SIMT batched GEMM at C2, scripts/debug/rot_bench.py); the small
+    # U <- U L stays a library batched GEMM pinned to full float32 (0.27 ms; own kernel measured 0.57 ms)
     with ops.fp32_matmul():
         u = torch.bmm(uf, lpad)  # (nb, b, rp)
-        v = torch.bmm(lmat.transpose(1, 2), vn)  # (nb, r, ld)
+        if r % 2 == 0:
+            v = ops.block_project_tc(vn, r * ld, ld, r, torch.zeros((nb, 2), dtype=torch.int32, device=dev), 1, r,
+                                     lpad[:, :r, :].contiguous(), r)  # (nb, r, ld)
+        else:
+            v = torch.bmm(lmat.transpose(1, 2), vn)  # (nb, r, ld)
     del uf, vn
     _submark("blocks.bmm_uv")
     if callable(thr_s):   # deferred threshold simulation (see simulate_thresholds): resolved here, where it is first needed

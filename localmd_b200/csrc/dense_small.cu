@@ -207,6 +207,9 @@ gram_dmma_kernel(const float* __restrict__ a, int n, int64_t m_len, int64_t bs, 
 // instructions per step and needs two barriers instead of three; the kernel is issue bound.
 // ------------------------------------------------------------------------------------------------
 constexpr int kJacThreads = 256;
+#ifdef PMD_TUNE
+__device__ unsigned long long g_jac_sweep_hist[2][64];   // development builds: histogram of sweeps used ([float32 sweeps?][count])
+#endif
 // 2 x 2 blocks per thread: (N/2)(N/2 + 1)/2 <= 528 for n <= 64 (3 items), <= 1596 for n <= 112 (7 items)
 
 template <typename S> struct JacVec;
@@ -347,6 +350,9 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
         }
         const int rots = n_rot;
         __syncthreads();
+#ifdef PMD_TUNE
+        if (tid == 0 && (rots == 0 || sweep == max_sweeps - 1)) atomicAdd(&g_jac_sweep_hist[sizeof(S) == 4][min(sweep + 1, 63)], 1ull);
+#endif
         if (rots == 0) break;
     }
 
@@ -402,6 +408,18 @@ extern "C" int pmd_gram_f64(const float* a, int64_t batch, int64_t n, int64_t m_
                                                                                  inner_stride, m_per, c);
     return pmd::check_launch(fn);
 }
+
+#ifdef PMD_TUNE
+extern "C" int pmd_debug_jacobi_hist(unsigned long long* out, int reset) {   // development builds only (not in the header)
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, pmd::g_jac_sweep_hist, sizeof(unsigned long long) * 128);
+    if (reset) {
+        unsigned long long z[128] = {0};
+        cudaMemcpyToSymbol(pmd::g_jac_sweep_hist, z, sizeof(z));
+    }
+    return 0;
+}
+#endif
 
 extern "C" int pmd_jacobi_eigh(double* c, int64_t batch, int64_t n, int mode, int sweeps_f32, double* w, float* vecs,
                                void* stream) {

@@ -424,17 +424,11 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
     _submark("blocks.jacobi2")
     lpad = torch.zeros((nb, rp, rp), dtype=torch.float32, device=dev)
     lpad[:, :r, :r] = lmat
-    # rotation into the singular vectors (decomposition.py:319-323).  V <- L^T V runs on the tensor cores through the block
-    # projection kernel: V[b] (r rows of ld frames) is a 1 x r "pixel block" of a pixel-major movie and L[b] its coefficient
-    # images (1.16 ms against 2.25 ms for the library's SIMT batched GEMM at C2, scripts/debug/rot_bench.py); the small
-    # U <- U L stays a library batched GEMM pinned to full float32 (0.27 ms; own kernel measured 0.57 ms)
+    # rotation into the singular vectors (decomposition.py:319-323): V <- L^T V on the tensor cores (_rows_times_coef_t); the
+    # small U <- U L stays a library batched GEMM pinned to full float32 (0.27 ms; own kernel measured 0.57 ms)
     with ops.fp32_matmul():
         u = torch.bmm(uf, lpad)  # (nb, b, rp)
-        if r % 2 == 0:
-            v = ops.block_project_tc(vn, r * ld, ld, r, torch.zeros((nb, 2), dtype=torch.int32, device=dev), 1, r,
-                                     lpad[:, :r, :].contiguous(), r)  # (nb, r, ld)
-        else:
-            v = torch.bmm(lmat.transpose(1, 2), vn)  # (nb, r, ld)
+    v = _rows_times_coef_t(lpad[:, :r, :], vn, r)  # (nb, r, ld)
     del uf, vn
     _submark("blocks.bmm_uv")
     if callable(thr_s):   # deferred threshold simulation (see simulate_thresholds): resolved here, where it is first needed
@@ -442,6 +436,19 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
     sstat, tstat, ranks = ops.block_stats_rank(u, v, bh, bw, r, thr_s, thr_t, mcf, t=t)
     _submark("blocks.stats")
     return u, v, ranks, sstat, tstat
+
+
+def _rows_times_coef_t(coef, v, r):
+    """out[b] = coef[b][:, :r]^T v[b]  for coef (nb, r, rp) (zero padded columns) and v (nb, r, ld): the r x r mixing of every
+    block's temporal rows.  Runs on the tensor cores through the block projection kernel -- v[b] is a 1 x r "pixel block"
+    of a pixel-major movie whose coefficient images are the columns of coef[b] (1.16 ms against 2.25 ms for the library's
+    SIMT batched GEMM at C2, scripts/debug/rot_bench.py); odd r (no even-width TMA box) falls back to the library."""
+    nb, _, ld = v.shape
+    if r % 2 == 0:
+        return ops.block_project_tc(v, r * ld, ld, r, torch.zeros((nb, 2), dtype=torch.int32, device=v.device), 1, r,
+                                    coef.contiguous(), r)
+    with ops.fp32_matmul():
+        return torch.bmm(coef[:, :, :r].transpose(1, 2), v)
 
 
 def _append_components(final, counter, comps, n_new):
@@ -483,8 +490,6 @@ def block_decompositions_windowed(yt, t, d2, starts_dev, bh, bw, r, taf, saf, th
     counter = torch.zeros((nb,), dtype=torch.int64, device=dev)
     sstat = torch.zeros((nb, r), dtype=torch.float32, device=dev)
     tstat = torch.zeros((nb, r), dtype=torch.float32, device=dev)
-    qi, qj = torch.arange(bpix, device=dev) // bw, torch.arange(bpix, device=dev) % bw
-    pix = (starts_dev[:, 0:1].to(torch.int64) + qi[None, :]) * d2 + starts_dev[:, 1:2].to(torch.int64) + qj[None, :]  # (nb, bpix)
     for wi, k in enumerate(start_points):
         active = counter < r
         if not bool(active.any()):
@@ -508,36 +513,47 @@ def block_decompositions_windowed(yt, t, d2, starts_dev, bh, bw, r, taf, saf, th
                 sstat[ia], tstat[ia] = ss_a, ts_a
             del u_a
         ib = torch.nonzero(resid).reshape(-1)
-        for c0 in range(0, int(ib.numel()), 1024):   # bounded working set: (1024, bpix, window) floats per slab
-            ic = ib[c0 : c0 + 1024]
-            n = int(ic.numel())
-            e = final[ic]                                            # (n, bpix, rp), columns >= counter are zero
-            blk = yw[pix[ic]]                                        # (n, bpix, ldw)
-            blk.baddbmm_(e, torch.bmm(e.transpose(1, 2), blk), alpha=-1.0)   # residual block (decomposition.py:362-364)
-            avg = blk[:, :, :window].reshape(n, bpix, window // taf, taf).mean(dim=3)   # (n, bpix, t')
-            skc = sk[ic]
+        if ib.numel():
+            # single_residual_block_md (decomposition.py:333-387) for all residual blocks at once, WITHOUT materialising the
+            # residual blocks: with E = the components kept so far (orthonormal columns) and W = E^T block,
+            #   time average of the residual  = tavg(block) - E tavg(W)                (averaging is linear)
+            #   U_b^T residual                = U_b^T block - (U_b^T E) W
+            # so the movie is only touched by the block kernels (pooling entry point with a 1 x 1 spatial window, tensor-core
+            # block projection); what remains are products of per-block r x r / bpix x r matrices.
+            n = int(ib.numel())
+            st_b = starts_dev[ib].contiguous()
+            e = final[ib].contiguous()                                               # (n, bpix, rp), columns >= counter are zero
+            w_e = ops.block_project_tc(yw, 0, ldw, d2, st_b, bh, bw, e, r)            # (n, r, ldw) = E^T block
+            avg = ops.block_pool_tavg(yw, window, d2, st_b, bh, bw, 1, taf)           # (n, bpix, t') = tavg(block)
+            we_avg = w_e[:, :, :window].reshape(n, r, window // taf, taf).mean(dim=3)
+            skc = sk[ib].contiguous()
             l = skc.shape[2]
-            if bpix > l:
-                y = torch.bmm(avg, skc)
-                q = ops.block_orth(y) if ops.block_orth_fits(bpix, l) else ops.orthonormalize_cols(y)
-                bq = torch.bmm(q.transpose(1, 2), avg).contiguous()
-                _, ev = ops.jacobi_eigh(ops.gram_rows(bq), mode=0)
-                u_b = torch.bmm(q, ev[:, :, :r])                     # (n, bpix, r)
-            else:
-                if r > bpix:
-                    raise TypeError("max_components larger than the block (jax.lax.dynamic_slice would fail)")
-                _, ev = ops.jacobi_eigh(ops.gram_rows(avg.contiguous()), mode=0)
-                u_b = ev[:, :, :r]
-            v_b = torch.bmm(u_b.transpose(1, 2), blk).contiguous()   # (n, r, ldw)
-            u_pad = torch.zeros((n, bpix, rp), dtype=torch.float32, device=dev)
-            u_pad[:, :, :r] = u_b
+            with ops.fp32_matmul():
+                avg.baddbmm_(e[:, :, :r], we_avg, alpha=-1.0)                         # decomposition.py:362-366
+                if bpix > l:
+                    y = torch.bmm(avg, skc)
+                    q = ops.block_orth(y) if ops.block_orth_fits(bpix, l) else ops.orthonormalize_cols(y)
+                    bq = torch.bmm(q.transpose(1, 2), avg).contiguous()
+                    _, ev = ops.jacobi_eigh(ops.gram_rows(bq), mode=0)
+                    u_b = torch.bmm(q, ev[:, :, :r])                                  # (n, bpix, r)
+                    del y, q, bq
+                else:
+                    if r > bpix:
+                        raise TypeError("max_components larger than the block (jax.lax.dynamic_slice would fail)")
+                    _, ev = ops.jacobi_eigh(ops.gram_rows(avg.contiguous()), mode=0)
+                    u_b = ev[:, :, :r]
+                u_pad = torch.zeros((n, bpix, rp), dtype=torch.float32, device=dev)
+                u_pad[:, :, :r] = u_b
+                coef = torch.bmm(e[:, :, :r].transpose(1, 2), u_pad)                  # (n, r, rp) = E^T U_b
+            v_b = ops.block_project_tc(yw, 0, ldw, d2, st_b, bh, bw, u_pad, r)        # (n, r, ldw) = U_b^T block
+            v_b -= _rows_times_coef_t(coef, w_e, r)                                   # ... - (U_b^T E) W
             _, _, rk_b = ops.block_stats_rank(u_pad, v_b, bh, bw, r, thr_s, thr_t, mcf, t=window)
-            n_new = torch.minimum(rk_b.to(torch.int64), r - counter[ic])
-            fb, cb = final[ic], counter[ic]
+            n_new = torch.minimum(rk_b.to(torch.int64), r - counter[ib])
+            fb, cb = final[ib], counter[ib]
             _append_components(fb, cb, u_pad, n_new)
-            final[ic] = fb
-            counter[ic] = cb + n_new
-            del blk, avg, u_b, v_b, u_pad
+            final[ib] = fb
+            counter[ib] = cb + n_new
+            del avg, u_b, v_b, u_pad, w_e, e
         del yw
     v = ops.block_project_tc(yt, 0, ld, d2, starts_dev, bh, bw, final, r)   # (nb, r, ld)
     return final, v, counter.to(torch.int32), sstat, tstat

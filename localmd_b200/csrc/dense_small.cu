@@ -108,9 +108,11 @@ gram_f64_kernel(const float* __restrict__ a, int n, int64_t m_len, int64_t bs, i
 constexpr int kDGK = 64;                 // inner-dimension values per shared-memory tile
 constexpr int kDGLd = kDGK + 4;          // row pitch in floats
 constexpr int kDGThreads = 256;
-constexpr int kDGMaxTiles = 14;          // ceil(14 * 15 / 2 / 8) upper-triangle tiles per warp for n <= 112
-
-__global__ void __launch_bounds__(kDGThreads)
+// kDGMaxTiles = upper-triangle 8 x 8 tiles per warp: ceil(14 * 15 / 2 / 8) = 14 for n <= 112, 4 for n <= 56 (the block
+// stage's n = 50: 28 tiles on 8 warps) -- the small variant needs 60 instead of 125 registers, which lifts the
+// register-limited residency from 2 to 4 CTAs per SM (ncu: tensor pipe 44 % active, long-scoreboard stalls on the tile loads)
+template <int kDGMaxTiles>
+__global__ void __launch_bounds__(kDGThreads, kDGMaxTiles <= 4 ? 4 : 2)
 gram_dmma_kernel(const float* __restrict__ a, int n, int64_t m_len, int64_t bs, int64_t rs, int64_t m_per_cta,
                  double* __restrict__ c) {
     extern __shared__ float dsm[];       // [8 * nt][kDGLd]
@@ -200,8 +202,8 @@ gram_dmma_kernel(const float* __restrict__ a, int n, int64_t m_len, int64_t bs, 
 //
 // A step rotates N / 2 disjoint index pairs I_k = (p_k, q_k) at once: A' = J^T A J, V' = V J.  Seen in 2 x 2 blocks,
 // A'[I_k, I_l] = J_k^T A[I_k, I_l] J_l, so the two-sided update is done in ONE pass with one thread per block: 4 loads,
-// both rotations in registers, and -- A being symmetric -- only the blocks k <= l are computed and written to both
-// triangles (the matrix stays exactly symmetric).  The eigenvector matrix is kept TRANSPOSED (row e = vector e), so
+// both rotations in registers, and -- A being symmetric -- only the blocks k <= l are computed and only the upper
+// triangle of A is kept (element (i, j) lives at [min(i, j)][max(i, j)]).  The eigenvector matrix is kept TRANSPOSED (row e = vector e), so
 // its column rotations are 16-byte vector operations on two contiguous rows.  Against the previous form (a column pass
 // over A and V with strided scalar accesses, a barrier, a row pass over A, a barrier) this issues ~2.3x fewer
 // instructions per step and needs two barriers instead of three; the kernel is issue bound.
@@ -315,22 +317,24 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
                 if (((pqk | pql) >> 16) == 0) continue;           // neither pair rotates
                 const int pk = pqk & 255, qk = (pqk >> 8) & 255, pl = pql & 255, ql = (pql >> 8) & 255;
                 const S ck = cc[k], sk = ss[k], cl = cc[l], sl = ss[l];
-                const S a00 = A[pk * ld + pl], a01 = A[pk * ld + ql], a10 = A[qk * ld + pl], a11 = A[qk * ld + ql];
+                // only the upper triangle of A is live: element (i, j) is kept at [min(i, j)][max(i, j)] (half the stores of
+                // a mirrored update; the kernel is bound by shared-memory bandwidth)
+                const int i00 = min(pk, pl) * ld + max(pk, pl), i01 = min(pk, ql) * ld + max(pk, ql);
+                const int i10 = min(qk, pl) * ld + max(qk, pl), i11 = min(qk, ql) * ld + max(qk, ql);
+                const S a00 = A[i00], a01 = A[i01], a10 = A[i10], a11 = A[i11];   // k == l: i10 == i01
                 // columns:  t_i0 = cl a_i0 - sl a_i1,  t_i1 = sl a_i0 + cl a_i1
                 const S t00 = cl * a00 - sl * a01, t01 = sl * a00 + cl * a01;
                 const S t10 = cl * a10 - sl * a11, t11 = sl * a10 + cl * a11;
                 // rows:     b_0j = ck t_0j - sk t_1j,  b_1j = sk t_0j + ck t_1j
-                S b00 = ck * t00 - sk * t10, b01 = ck * t01 - sk * t11;
-                S b10 = sk * t00 + ck * t10, b11 = sk * t01 + ck * t11;
+                const S b00 = ck * t00 - sk * t10, b01 = ck * t01 - sk * t11;
+                const S b10 = sk * t00 + ck * t10, b11 = sk * t01 + ck * t11;
+                A[i00] = b00;
+                A[i11] = b11;
                 if (k == l) {
-                    b01 = b10 = (S)0;                              // the annihilated element
-                    A[pk * ld + pk] = b00;
-                    A[qk * ld + qk] = b11;
-                    A[pk * ld + qk] = b01;
-                    A[qk * ld + pk] = b10;
+                    A[i01] = (S)0;                                 // the annihilated element (p_k < q_k: i01 is its upper copy)
                 } else {
-                    A[pk * ld + pl] = b00; A[pk * ld + ql] = b01; A[qk * ld + pl] = b10; A[qk * ld + ql] = b11;
-                    A[pl * ld + pk] = b00; A[ql * ld + pk] = b01; A[pl * ld + qk] = b10; A[ql * ld + qk] = b11;
+                    A[i01] = b01;
+                    A[i10] = b10;
                 }
             }
             // V' = V J on the transposed copy: rows p_k, q_k
@@ -392,11 +396,11 @@ extern "C" int pmd_gram_f64(const float* a, int64_t batch, int64_t n, int64_t m_
         // contiguous rows: FP64 tensor cores
         const int nt8 = (int)(n + 7) / 8;
         const size_t smem_d = (size_t)8 * nt8 * pmd::kDGLd * sizeof(float);
-        cudaError_t e2 = cudaFuncSetAttribute(pmd::gram_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
+        auto kern = nt8 * (nt8 + 1) / 2 <= 32 ? pmd::gram_dmma_kernel<4> : pmd::gram_dmma_kernel<14>;
+        cudaError_t e2 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d);
         if (e2 != cudaSuccess) { pmd::set_error(std::string(fn) + ": " + cudaGetErrorString(e2)); return (int)e2; }
         dim3 grid_d((unsigned)splits, (unsigned)batch);
-        pmd::gram_dmma_kernel<<<grid_d, pmd::kDGThreads, smem_d, (cudaStream_t)stream>>>(a, (int)n, m_len, batch_stride, row_stride,
-                                                                                      m_per, c);
+        kern<<<grid_d, pmd::kDGThreads, smem_d, (cudaStream_t)stream>>>(a, (int)n, m_len, batch_stride, row_stride, m_per, c);
         return pmd::check_launch(fn);
     }
     const int nt = (int)(n + 1) / 2;

@@ -375,7 +375,9 @@ def matmul_3xtf32_any(a, b):
 
 def block_orth_fits(m, n):
     """True when an (m, n) matrix (+ its float64 Gram) fits the shared memory of pmd_block_orth."""
-    return n <= 64 and (n * (n | 1) + 2 * n) * 8 + m * (n | 1) * 4 <= 227 * 1024
+    n4, n8, m8 = (n + 3) // 4 * 4, (n + 7) // 8 * 8, (m + 7) // 8 * 8
+    ldg = n8 if n8 & 8 else n8 + 8
+    return n <= 64 and (n8 * ldg + 3 * n8) * 8 + m8 * n4 * 4 <= 227 * 1024
 
 
 def block_orth(x, ncols=None, g_ext=None, passes=2):

@@ -19,3 +19,24 @@ for n, m, f32 in ((50, 5000, False), (60, 500, True)):
         e1.record()
         torch.cuda.synchronize()
     print("jacobi n=%d f32=%s: %.3f ms" % (n, f32, e0.elapsed_time(e1)))
+for (m, n, ld) in ((400, 50, 52), (100, 60, 60)):
+    s = torch.randn(nb, m, ld, device="cuda")
+    s[:, :, n:] = 0
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sc = s.clone()
+        torch.cuda.synchronize()
+        e0.record()
+        ops.block_orth(sc, n)
+        e1.record()
+        torch.cuda.synchronize()
+    print("block_orth m=%d n=%d: %.3f ms" % (m, n, e0.elapsed_time(e1)))
+x = torch.randn(nb, 50, 5000, device="cuda")
+for _ in range(2):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    ops.gram_rows(x)
+    e1.record()
+    torch.cuda.synchronize()
+print("gram_rows n=50 m=5000: %.3f ms" % e0.elapsed_time(e1))

@@ -589,6 +589,7 @@ class SparseU:
         self._ts_future = None
         self._utu_future = None
         self._tables_started = False
+        self.idle_hook = None
         which = os.environ.get("PMD_K7", "ts")   # development switch between the generations of the projection kernel
         self._want_ts = bool(regular and which == "ts")
         if self._want_ts:
@@ -730,6 +731,8 @@ class SparseU:
             c = ops.project_cols_f64(bg64, self.d2, self.starts_dev, self.bh, self.bw, blk_of_col, self.col0_dev, self.uvals64,
                                      bg64)  # (n_cols, K)
             if self.n_local > 0:
+                if self.idle_hook is not None:      # the launching thread is about to wait for the worker: enqueue side work
+                    self.idle_hook()
                 host = self._utu_future.result() if self._utu_future is not None else None
                 self._utu_future = None
                 csr = ops.utu_local_csr(self.starts, self.starts_dev, self.bh, self.bw, self.ranks_host, self.ranks_dev,
@@ -1109,6 +1112,17 @@ def localmd_decomposition(
         dim_1_iters, dim_2_iters = tile_starts(d1, bh), tile_starts(d2, bw)
         starts = np.stack(np.meshgrid(dim_1_iters, dim_2_iters, indexing="ij"), axis=-1).reshape(-1, 2).astype(np.int32)
         nb = starts.shape[0]
+        # summed pyramid weights of the covering blocks: sum_b shift(block_weights) = Rm^T W Cm with the 0/1
+        # incidence matrices of (block-local row, FOV row) and (block-local column, FOV column); exact in float64.
+        # (Rank independent host work: done HERE, before the init filter is enqueued -- the table uploads further down drain
+        # the stream, and 1.2 ms of NumPy between that drain and the first block kernel left the device idle.)
+        block_weights = pyramid_weights(bh, bw)
+        rm, cm = np.zeros((bh, d1)), np.zeros((bw, d2))
+        for q in range(bh):
+            rm[q, np.asarray(dim_1_iters) + q] = 1.0
+        for q in range(bw):
+            cm[q, np.asarray(dim_2_iters) + q] = 1.0
+        cumw = rm.T @ block_weights.astype(np.float64) @ cm
         # blocks are partitioned over the ranks (contiguous index ranges); results are all-gathered below
         b0, b1 = sharding.block_partition(nb, world)[rank]
         row_lo, row_hi = 0, d1                                   # image rows of the init movie this rank holds
@@ -1164,17 +1178,6 @@ def localmd_decomposition(
         starts_dev = ops.h2d(starts, dev)
         # block origins relative to the rows of the init movie this rank holds
         starts_fit = starts_dev if row_lo == 0 else (starts_dev - ops.h2d(np.array([row_lo, 0], dtype=np.int32), dev))
-        block_weights = pyramid_weights(bh, bw)
-        # summed pyramid weights of the covering blocks: sum_b shift(block_weights) = Rm^T W Cm with the 0/1
-        # incidence matrices of (block-local row, FOV row) and (block-local column, FOV column); exact in float64.
-        # (Rank independent: computed and uploaded here, while the device is busy with the init filter, not after the
-        # rank decision, where the device would wait for the host.)
-        rm, cm = np.zeros((bh, d1)), np.zeros((bw, d2))
-        for q in range(bh):
-            rm[q, np.asarray(dim_1_iters) + q] = 1.0
-        for q in range(bw):
-            cm[q, np.asarray(dim_2_iters) + q] = 1.0
-        cumw = rm.T @ block_weights.astype(np.float64) @ cm
         block_weights_dev = ops.h2d(block_weights.reshape(-1), dev)
         cumw_dev = ops.h2d(cumw.reshape(-1), dev)
 
@@ -1244,6 +1247,25 @@ def localmd_decomposition(
                                        max_rank=int(ranks_host.max()))
         tm.mark("assemble")
 
+        # ---- result CSR on a side stream -------------------------------------------------------------
+        # The relabelled CSR of U (sorts / scatters, ~3.4 ms at C2) only depends on the assembled components.  It is enqueued
+        # where the launching thread would otherwise WAIT for the worker's U^T U tables (SparseU.idle_hook, inside the
+        # whitening: 1.2 ms of idle device in the job timeline), and runs beside the whitening's float64 kernels.
+        main = torch.cuda.current_stream(dev)
+        side = _side_stream(dev)
+        row_ids = ops.h2d(np.arange(d).reshape((d1, d2), order=order).reshape(-1), dev)
+        csr_out = {}
+
+        def start_csr():
+            if csr_out:
+                return
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                csr_out["csr"] = su.csr(row_ids)
+                csr_out["csr32"] = su.csr_physical32()
+
+        su.idle_hook = start_csr
+
         # ---- orthogonalisation (decomposition.py:860-881) -------------------------------------------
         if rank_prune:
             if rank_prune_factor <= 0 or rank_prune_factor > 1:
@@ -1271,24 +1293,9 @@ def localmd_decomposition(
         v_full = project_movie(movie, su, p, mean, inv_std)
         tm.mark("projection")
 
-        # ---- result CSR on a side stream -------------------------------------------------------------
-        # The relabelled CSR of U (sorts / scatters, ~3.4 ms at C2) only depends on the assembled components: it runs
-        # beside the final SVD, whose float64 eigensolver leaves most of the GPU idle.
-        main = torch.cuda.current_stream(dev)
-        side = _side_stream(dev)
-        row_ids = ops.h2d(np.arange(d).reshape((d1, d2), order=order).reshape(-1), dev)
-        csr_out = {}
-
-        def start_csr():
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                csr_out["csr"] = su.csr(row_ids)
-                csr_out["csr32"] = su.csr_physical32()
-
         # ---- final SVD (decomposition.py:896-904) ---------------------------------------------------
-        rmix, s, vt = projected_svd(p, v_full, group, after_gram=start_csr)
-        if not csr_out:          # k > T path of projected_svd: no Gram hook
-            start_csr()
+        start_csr()              # (no-op when the whitening already started it)
+        rmix, s, vt = projected_svd(p, v_full, group)
         indptr, indices, values = csr_out["csr"]
         csr32 = csr_out["csr32"]
         for t_ in (indptr, indices, values) + tuple(csr32):

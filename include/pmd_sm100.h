@@ -423,6 +423,21 @@ int pmd_split_tf32_bf16(float* x, int64_t rows, int64_t cols, int64_t ldx, void*
 int pmd_sym_product_f64(const void* a, int a_dtype, int64_t lda, const void* b, int b_dtype, int64_t ldb, int layout,
                         int64_t n, int64_t k_len, int64_t splits, double* work, double* c, void* stream);
 
+/* CSR export of U straight from the block-component form: canonical CSR (rows = pixels, ascending columns, exact zeros
+ * dropped) in two passes of one thread per pixel.  Block grid = row_starts [n_br] x col_starts [n_bc] (ascending; block
+ * b = ri * n_bc + ci), kept ranks [nb], first column col0 [nb], weighted values uvals [(col0[b] + c) * bh*bw + q] float64,
+ * dense background rows bg [K][d] float32 as columns n_local .. n_local + K - 1.  Two row numberings are produced at once:
+ * "rel" (row id = row_ids[p], e.g. the reference's order="F" pixel numbering; row_ids NULL = physical) with float64 values
+ * and "phys" (row id = p = i * d2 + j) with float32 values (what pmd_reconstruct reads).
+ *   fill = 0: counts_rel [d], counts_phys [d] = entries per row (the caller turns them into indptr by a prefix sum)
+ *   fill = 1: cols / vals written at indptr_rel[row] .. / indptr_phys[row] ..
+ * replaces: decomposition.py:811-857 (coo triplets -> csr) and 912-933 (aggregate_decomposition: background columns). */
+int pmd_export_csr(const double* uvals, const float* bg, int64_t K, int64_t d1, int64_t d2, const int32_t* row_starts,
+                   int64_t n_br, const int32_t* col_starts, int64_t n_bc, int64_t bh, int64_t bw, const int32_t* ranks,
+                   const int64_t* col0, int64_t n_local, const int64_t* row_ids, int fill, int64_t* counts_rel,
+                   int64_t* counts_phys, const int64_t* indptr_rel, const int64_t* indptr_phys, int32_t* cols_rel,
+                   double* vals_rel, int32_t* cols_phys, float* vals_phys, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpmd_sm100.so")
-SOURCES = ["capi.cu", "stats.cu", "stats_fft.cu", "stats_tc.cu", "dense_small.cu", "orth.cu", "blocks.cu", "blocks_t.cu", "blocks_tc.cu", "blocks_ts.cu", "bgfilter.cu", "bgbasis.cu", "split.cu", "project.cu", "project_stream.cu", "project_tc.cu", "project_ts.cu", "strips_ts_host.cu", "strips_host.cu", "strips_tc_host.cu", "reconstruct.cu", "whiten.cu", "sym_f64.cu"]
+SOURCES = ["capi.cu", "stats.cu", "stats_fft.cu", "stats_tc.cu", "dense_small.cu", "orth.cu", "blocks.cu", "blocks_t.cu", "blocks_tc.cu", "blocks_ts.cu", "bgfilter.cu", "bgbasis.cu", "split.cu", "project.cu", "project_stream.cu", "project_tc.cu", "project_ts.cu", "strips_ts_host.cu", "strips_host.cu", "strips_tc_host.cu", "reconstruct.cu", "whiten.cu", "sym_f64.cu", "export_csr.cu"]
 NVCC_FLAGS = ([f for f in os.environ.get("PMD_NVCC_EXTRA", "").split() if f]) + [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-diag-suppress", "550",

@@ -16,6 +16,7 @@ import contextlib
 import datetime
 import math
 import os
+import time
 import sys
 from typing import Callable, Optional
 
@@ -127,6 +128,14 @@ def _side_stream(dev, priority=0):
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev, priority=priority)
     return _SIDE_STREAMS[key]
+
+
+_HOST_TRACE = [] if os.environ.get("PMD_HOST_TRACE") else None   # development: host wall-clock marks of one job
+
+
+def _ht(label):
+    if _HOST_TRACE is not None:
+        _HOST_TRACE.append((label, time.perf_counter()))
 
 
 def _submark(name):
@@ -587,9 +596,8 @@ class SparseU:
         self._tc_host = None
         self._ts_host = None
         self._ts_future = None
-        self._utu_future = None
+        self._utu_host = None
         self._tables_started = False
-        self.idle_hook = None
         which = os.environ.get("PMD_K7", "ts")   # development switch between the generations of the projection kernel
         self._want_ts = bool(regular and which == "ts")
         if self._want_ts:
@@ -604,15 +612,17 @@ class SparseU:
             self._build_supertiles()
 
     def start_host_tables(self):
-        """Hand the host-side tables to the worker thread (idempotent): the block-pair bookkeeping of U^T U (whitening,
-        NumPy) and the strip tables of K7 (native routine of the library, releases the GIL).  The driver calls this AFTER
-        it has enqueued the prune-sketch GEMMs, so that the worker's GIL-holding NumPy steps compete with a main thread
-        that has device work queued, not with one the device is waiting for."""
+        """Host-side tables that depend on the kept ranks (idempotent): the block-pair bookkeeping of U^T U (whitening) inline,
+        the strip tables of K7 (3 ms, native routine of the library, releases the GIL) on the worker thread.  The driver calls
+        this AFTER it has enqueued the prune-sketch GEMMs, so that the device has work queued meanwhile."""
         if self._tables_started:
             return
         self._tables_started = True
         if self.n_local > 0:
-            self._utu_future = _HOST_POOL.submit(ops.utu_host_tables, self.starts, self.bh, self.bw, self.ranks_host.copy())
+            # 0.2 ms of (mostly native) work once the block-pair list is memoised: done inline -- on the worker thread the
+            # result arrived 4.4 ms after it was requested (the worker has to win the interpreter lock from the launching
+            # thread first), and the device idled for 3 ms waiting for it
+            self._utu_host = ops.utu_host_tables(self.starts, self.bh, self.bw, self.ranks_host)
         if self._want_ts:
             # K7 with TMA-fed raw tiles and the movie operand in tensor memory (csrc/project_ts.cu): host tables on the worker,
             # device tables and coefficient images at the first projection call
@@ -718,6 +728,25 @@ class SparseU:
         vals_new[pos] = vals
         return indptr_new, cols_new, vals_new
 
+    def export_csr(self, row_ids):
+        """((indptr, indices, values64) with rows relabelled by row_ids, (indptr, indices, values32) over physical rows): on a
+        regular block grid written directly by pmd_export_csr (no coordinate list, no sort; the buffers are sliced to the
+        true number of entries by finish_export), otherwise through the sorted coordinate form (csr / csr_physical32)."""
+        if self._regular is None or len(self.ranks_host) == 0 or self.bg.shape[0] == 0:
+            return self.csr(row_ids), self.csr_physical32()
+        rows, cols = self._regular
+        return ops.export_csr(self.uvals64, self.bg, self.d1, self.d2, rows, cols, self.bh, self.bw, self.ranks_dev, self.col0_dev,
+                              self.n_local, row_ids)
+
+    @staticmethod
+    def finish_export(exported):
+        """Slice the worst-case buffers of export_csr to the true entry count (one read-back of indptr[-1])."""
+        (ip, ix, v), (ip32, ix32, v32) = exported
+        nnz = int(ip32[-1].item())
+        if ix.numel() != nnz:
+            ix, v, ix32, v32 = ix[:nnz], v[:nnz], ix32[:nnz], v32[:nnz]
+        return (ip, ix, v), (ip32, ix32, v32)
+
     def gram(self):
         """U^T U in float64 as (CSR of the local x local part, C = U^T bg^T (n_cols, K)): the two sparse products
         of decomposition.py:974-981 reduce to applying these to the right factor."""
@@ -731,10 +760,7 @@ class SparseU:
             c = ops.project_cols_f64(bg64, self.d2, self.starts_dev, self.bh, self.bw, blk_of_col, self.col0_dev, self.uvals64,
                                      bg64)  # (n_cols, K)
             if self.n_local > 0:
-                if self.idle_hook is not None:      # the launching thread is about to wait for the worker: enqueue side work
-                    self.idle_hook()
-                host = self._utu_future.result() if self._utu_future is not None else None
-                self._utu_future = None
+                host, self._utu_host = self._utu_host, None
                 csr = ops.utu_local_csr(self.starts, self.starts_dev, self.bh, self.bw, self.ranks_host, self.ranks_dev,
                                         self.col0_host, self.col0_dev, self.uvals64, host=host)
             else:
@@ -828,7 +854,7 @@ class SparseU:
         ops.project_dense(movie2d, self.bg, mean, inv_std, zb)
 
 
-def compute_lowrank_factorized_svd(u, v, only_left=False, factor="eigh"):
+def compute_lowrank_factorized_svd(u, v, only_left=False, factor="eigh", before_wait=None):
     """decomposition.py:936-1010 on the GPU.  `u` is a SparseU (or a scipy sparse matrix, converted),
     `v` a dense (R, t') tensor/array.  Returns the spatial mixing matrix P (R, k) (device tensor) such
     that U P has orthonormal columns; with only_left=False also (s, Vt) of the factorised product.
@@ -856,6 +882,8 @@ def compute_lowrank_factorized_svd(u, v, only_left=False, factor="eigh"):
         # the triangular solve is enqueued before the verdict is read back (the read is a host synchronisation; the device
         # keeps working through it) and discarded in the rare singular case
         spec = torch.linalg.solve_triangular(chol.t(), right, upper=True, left=False)   # X L^T = M (2.0 ms; L X^T = M^T: 2.7 ms)
+        if before_wait is not None:     # the launching thread is about to wait for the device: the caller's cue for host work
+            before_wait()
         if bool(ok.item()):
             mix64 = spec
             _submark("whiten.chol")
@@ -1218,6 +1246,7 @@ def localmd_decomposition(
                 sstat = sharding.ragged_all_gather(sstat.contiguous(), bcounts, group)
                 tstat = sharding.ragged_all_gather(tstat.contiguous(), bcounts, group)
         ranks_host = ranks_dev.cpu().numpy().astype(np.int64)
+        _ht("ranks_host")
         tm.mark("blocks")
 
         # ---- weighted sparse assembly (decomposition.py:811-857) -----------------------------------
@@ -1230,6 +1259,7 @@ def localmd_decomposition(
         )
         # (output_size: without it repeat_interleave reads the total back from the device -- a host synchronisation)
         blk_of_col = torch.repeat_interleave(torch.arange(b1 - b0, device=dev), ranks_loc.to(torch.int64), output_size=ncol_loc)
+        _ht("assemble_u enqueued")
         comp_of_col = torch.arange(ncol_loc, device=dev) - col0_loc[blk_of_col]
         v_loc = v_blk[blk_of_col, comp_of_col][:, :crop].contiguous()  # (local columns, t)
         del u_blk, v_blk, yt
@@ -1239,6 +1269,7 @@ def localmd_decomposition(
             uv32 = sharding.ragged_all_gather(uv32, ccounts, group)
             v_loc = sharding.ragged_all_gather(v_loc, ccounts, group)
         su = SparseU(starts, starts_dev, bh, bw, d1, d2, ranks_host, ranks_dev, uv64, uv32, bg)
+        _ht("SparseU built")
         v_init = torch.cat([v_loc, vbg[:, :crop]], dim=0)  # (R, t)
         del v_loc
         say("The total rank before pruning is {}".format(su.n_cols))
@@ -1246,25 +1277,13 @@ def localmd_decomposition(
             timings["__info__"] = dict(n_cols=int(su.n_cols), n_local=int(su.n_local), nb=int(nb), mean_rank=float(ranks_host.mean()),
                                        max_rank=int(ranks_host.max()))
         tm.mark("assemble")
+        _ht("assemble mark")
 
-        # ---- result CSR on a side stream -------------------------------------------------------------
-        # The relabelled CSR of U (sorts / scatters, ~3.4 ms at C2) only depends on the assembled components.  It is enqueued
-        # where the launching thread would otherwise WAIT for the worker's U^T U tables (SparseU.idle_hook, inside the
-        # whitening: 1.2 ms of idle device in the job timeline), and runs beside the whitening's float64 kernels.
-        main = torch.cuda.current_stream(dev)
-        side = _side_stream(dev)
+        # ---- result CSR (decomposition.py:811-857, 912-933) --------------------------------------------
+        # Written straight from the block-component form by two small kernels (count, fill) as soon as the components are
+        # assembled; the worst-case buffers are sliced to the true entry count at the very end (finish_export).
         row_ids = ops.h2d(np.arange(d).reshape((d1, d2), order=order).reshape(-1), dev)
-        csr_out = {}
-
-        def start_csr():
-            if csr_out:
-                return
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                csr_out["csr"] = su.csr(row_ids)
-                csr_out["csr32"] = su.csr_physical32()
-
-        su.idle_hook = start_csr
+        exported = su.export_csr(row_ids)
 
         # ---- orthogonalisation (decomposition.py:860-881) -------------------------------------------
         if rank_prune:
@@ -1280,7 +1299,9 @@ def localmd_decomposition(
             else:
                 ps = torch.randn(shape, generator=gen, device=dev, dtype=torch.float32)
             # the prune sketch V Omega (R x t)(t x k'): float32-accurate on the tensor cores (3xTF32) instead of a SIMT GEMM
+            _ht("prune sketch drawn")
             sketch = ops.matmul_3xtf32_any(v_init, ps)
+            _ht("prune GEMM enqueued")
             su.start_host_tables()   # worker thread: U^T U bookkeeping + K7 strip tables, beside the GEMMs just enqueued
             p = compute_lowrank_factorized_svd(su, sketch, only_left=True, factor="chol")
             del sketch
@@ -1288,31 +1309,33 @@ def localmd_decomposition(
             p = compute_lowrank_factorized_svd(su, v_init, only_left=True, factor="chol")
         say("After performing rank reduction, the updated rank is {}".format(p.shape[1]))
         tm.mark("whiten")
+        _ht("whiten enqueued")
 
         # ---- full-movie projection (pmd_loader.py:316-346) ------------------------------------------
         v_full = project_movie(movie, su, p, mean, inv_std)
         tm.mark("projection")
+        _ht("projection enqueued")
 
         # ---- final SVD (decomposition.py:896-904) ---------------------------------------------------
-        start_csr()              # (no-op when the whitening already started it)
         rmix, s, vt = projected_svd(p, v_full, group)
-        indptr, indices, values = csr_out["csr"]
-        csr32 = csr_out["csr32"]
-        for t_ in (indptr, indices, values) + tuple(csr32):
-            t_.record_stream(main)
         good = s != 0
         rmix, s, vt = rmix[:, good], s[good], vt[good, :]
         if group is not None:  # Vt column shards -> the full (k, T) factor on every rank
             fcounts = [hi_ - lo_ for lo_, hi_ in bounds]
             vt = sharding.ragged_all_gather(vt.t().contiguous(), fcounts, group).t().contiguous()
         tm.mark("final_svd")
+        _ht("final_svd enqueued")
 
         # ---- result object ---------------------------------------------------------------------------
-        main.wait_stream(side)
+        (indptr, indices, values), csr32 = SparseU.finish_export(exported)
         out = PMDArray._from_device((indptr, indices, values), csr32, rmix.contiguous(), s.contiguous(),
                                     vt.contiguous(), (T, d1, d2), order, mean, std, dev)
         tm.mark("export")
         tm.finish()
+        if _HOST_TRACE is not None:
+            t0_ = _HOST_TRACE[0][1]
+            sys.stderr.write("host trace (ms): " + ", ".join("%s %.2f" % (l_, 1e3 * (t_ - t0_)) for l_, t_ in _HOST_TRACE) + "\n")
+            _HOST_TRACE.clear()
         if timings is not None and "__info__" in timings:
             timings["__info__"]["h2d_bytes"] = int(movie.h2d_bytes)
         _ACTIVE_TIMER = None

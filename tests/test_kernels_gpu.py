@@ -797,3 +797,30 @@ def test_sym_product_f64(ops, n, k, layout, dt):
     if layout == 0:
         again = ops.sym_product_f64(dev(a)).cpu().numpy()
         assert np.array_equal(got, again)                               # deterministic
+
+
+# ------------------------------------------------------------------------------------------------ CSR export
+@pytest.mark.parametrize("d1,d2,bh,bw,K,order", [(50, 44, 16, 12, 3, "F"), (40, 36, 16, 16, 2, "C"), (23, 31, 10, 14, 1, "F")])
+def test_export_csr_matches_sorted_coordinate_form(ops, d1, d2, bh, bw, K, order):
+    """pmd_export_csr (direct CSR from the block-component form) against the sorted coordinate form: identical indptr /
+    indices / values in both row numberings, exact zeros dropped, shifted last tiles (up to 3 x 3 covering blocks)."""
+    from localmd_b200.decomposition import SparseU, tile_starts
+
+    rng = np.random.default_rng(d1 * d2)
+    rows, cols = tile_starts(d1, bh), tile_starts(d2, bw)
+    starts = np.array([(r, c) for r in rows for c in cols], dtype=np.int32)
+    nb = len(starts)
+    ranks = rng.integers(0, 5, nb).astype(np.int64)
+    n_local = int(ranks.sum())
+    uv = rng.standard_normal((n_local, bh * bw))
+    uv[rng.random(uv.shape) < 0.1] = 0.0                      # exact zeros must be dropped
+    bg = rng.standard_normal((K, d1 * d2)).astype(np.float32)
+    bg[rng.random(bg.shape) < 0.05] = 0.0
+    uv64 = dev(uv)
+    su = SparseU(starts, dev(starts), bh, bw, d1, d2, ranks, dev(ranks.astype(np.int32)), uv64, uv64.to(torch.float32), dev(bg))
+    row_ids = dev(np.arange(d1 * d2).reshape((d1, d2), order=order).reshape(-1))
+    (ip, ix, v), (ip32, ix32, v32) = SparseU.finish_export(su.export_csr(row_ids))
+    wp, wx, wv = su.csr(row_ids)
+    pp, px, pv = su.csr_physical32()
+    assert torch.equal(ip, wp) and torch.equal(ix, wx) and torch.equal(v, wv)
+    assert torch.equal(ip32, pp) and torch.equal(ix32, px) and torch.equal(v32, pv)

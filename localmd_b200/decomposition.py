@@ -735,7 +735,10 @@ class SparseU:
         if self._regular is None or len(self.ranks_host) == 0 or self.bg.shape[0] == 0:
             return self.csr(row_ids), self.csr_physical32()
         rows, cols = self._regular
-        return ops.export_csr(self.uvals64, self.bg, self.d1, self.d2, rows, cols, self.bh, self.bw, self.ranks_dev, self.col0_dev,
+        # origins of the block rows / columns from the device copy of the block list (no upload, no synchronisation)
+        rs = self.starts_dev[:: len(cols), 0].contiguous()
+        cs = self.starts_dev[: len(cols), 1].contiguous()
+        return ops.export_csr(self.uvals64, self.bg, self.d1, self.d2, rs, cs, self.bh, self.bw, self.ranks_dev, self.col0_dev,
                               self.n_local, row_ids)
 
     @staticmethod
@@ -1282,7 +1285,10 @@ def localmd_decomposition(
         # ---- result CSR (decomposition.py:811-857, 912-933) --------------------------------------------
         # Written straight from the block-component form by two small kernels (count, fill) as soon as the components are
         # assembled; the worst-case buffers are sliced to the true entry count at the very end (finish_export).
-        row_ids = ops.h2d(np.arange(d).reshape((d1, d2), order=order).reshape(-1), dev)
+        if order == "F":     # row of U of physical pixel (i, j): i + j * d1 (pmdarray.py:37-38), formed on the device
+            row_ids = (torch.arange(d1, device=dev)[:, None] + d1 * torch.arange(d2, device=dev)[None, :]).reshape(-1).contiguous()
+        else:
+            row_ids = torch.arange(d, device=dev)
         exported = su.export_csr(row_ids)
 
         # ---- orthogonalisation (decomposition.py:860-881) -------------------------------------------

@@ -689,7 +689,8 @@ def export_csr(uvals64, bg, d1, d2, row_starts, col_starts, bh, bw, ranks, col0,
     _req(uvals64, torch.float64, "uvals64"), _req(bg, torch.float32, "bg"), _req(ranks, torch.int32, "ranks"), _req(col0, torch.int64, "col0")
     dev = uvals64.device
     d, K = d1 * d2, bg.shape[0]
-    rs, cs = h2d(np.asarray(row_starts, dtype=np.int32), dev), h2d(np.asarray(col_starts, dtype=np.int32), dev)
+    rs, cs = row_starts, col_starts     # int32 device tensors (ascending block-row / block-column origins)
+    _req(rs, torch.int32, "row_starts"), _req(cs, torch.int32, "col_starts")
     if row_ids is not None:
         _req(row_ids, torch.int64, "row_ids")
     counts = torch.empty((2, d), dtype=torch.int64, device=dev)

@@ -697,7 +697,8 @@ def export_csr(uvals64, bg, d1, d2, row_starts, col_starts, bh, bw, ranks, col0,
     args = (_p(uvals64), _p(bg), K, d1, d2, _p(rs), rs.numel(), _p(cs), cs.numel(), bh, bw, _p(ranks), _p(col0), n_local, _p(row_ids))
     _call("pmd_export_csr", *args, 0, _p(counts[0]), _p(counts[1]), None, None, None, None, None, None, _stream())
     indptr = torch.zeros((2, d + 1), dtype=torch.int64, device=dev)
-    torch.cumsum(counts, dim=1, out=indptr[:, 1:])
+    for i in range(2):   # two 1-D scans (the device-wide scan; a (2, d) scan along dim 1 runs as two single-CTA scans: 0.5 ms)
+        torch.cumsum(counts[i], dim=0, out=indptr[i, 1:])
     nnz_max = n_local * bh * bw + K * d
     cols = torch.empty((2, nnz_max), dtype=torch.int32, device=dev)
     vals64 = torch.empty(nnz_max, dtype=torch.float64, device=dev)

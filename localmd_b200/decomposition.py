@@ -270,12 +270,16 @@ def simulate_thresholds(bh, bw, t_win, sim_conf, draws, gen, device, iters=250, 
     n_iters = len(draws.sim_noise) if have_noise else iters
     for s0 in range(0, n_iters, chunk):
         m = min(chunk, n_iters - s0)
-        noise = torch.zeros((m, b, ld), dtype=torch.float32, device=device)
-        if have_noise:
-            for i in range(m):
-                noise[i, :, :t_win] = _as_dev(np.asarray(draws.sim_noise[s0 + i]).reshape(b, t_win), device)
+        if not have_noise and ld == t_win:
+            # drawn in place: zero fill + a temporary + a strided copy would move 8 GB instead of 2 GB at C2
+            noise = torch.empty((m, b, ld), dtype=torch.float32, device=device).normal_(generator=gen)
         else:
-            noise[:, :, :t_win] = torch.randn((m, b, t_win), generator=gen, device=device, dtype=torch.float32)
+            noise = torch.zeros((m, b, ld), dtype=torch.float32, device=device)
+            if have_noise:
+                for i in range(m):
+                    noise[i, :, :t_win] = _as_dev(np.asarray(draws.sim_noise[s0 + i]).reshape(b, t_win), device)
+            else:
+                noise[:, :, :t_win] = torch.randn((m, b, t_win), generator=gen, device=device, dtype=torch.float32)
         if have_sk:
             sk = torch.stack([_as_dev(draws.sim_sketch[s0 + i], device) for i in range(m)])
         else:
@@ -358,9 +362,21 @@ def block_decompositions(yt, t, d2, starts_dev, bh, bw, r, taf, saf, thr_s, thr_
     P = bta.shape[1]
     l = sketches.shape[2]
     if P > l:
-        y = torch.bmm(bta, sketches)  # (nb, P, l)
+        tq = bta.shape[2]
+        on_tc = l <= 64 and l % 4 == 0 and tq % 4 == 0 and pw % 2 == 0
+        if on_tc:
+            # both sketch products on the tensor cores through the block kernels: B_ta[b] (P pooled pixels x t' frames) is a
+            # ph x pw "block" of a pixel-major movie with batch stride P t' (0.15 + 0.1 ms against 0.4 + 0.4 ms for the
+            # library's SIMT batched GEMMs at C2)
+            zero_starts = torch.zeros((nb, 2), dtype=torch.int32, device=dev)
+            y = ops.block_spatial_tc(bta, P * tq, tq, pw, zero_starts, ph, pw, sketches.transpose(1, 2).contiguous(), l)  # (nb, P, l) = B_ta Omega
+        else:
+            y = torch.bmm(bta, sketches)  # (nb, P, l)
         q = ops.block_orth(y) if ops.block_orth_fits(P, l) else ops.orthonormalize_cols(y)
-        bq = torch.bmm(q.transpose(1, 2), bta).contiguous()  # (nb, l, t')
+        if on_tc:
+            bq = ops.block_project_tc(bta, P * tq, tq, pw, zero_starts, ph, pw, q, l)  # (nb, l, t') = Q^T B_ta
+        else:
+            bq = torch.bmm(q.transpose(1, 2), bta).contiguous()  # (nb, l, t')
         # sketch-stage SVD (decomposition.py:66): float32 rotations on the float64 Gram, the accuracy of the reference's
         # own float32 SVD; its output only seeds the temporal basis that the full-resolution steps below refine
         _, e = ops.jacobi_eigh(ops.gram_rows(bq), mode=0, sweeps_f32=True)

@@ -836,8 +836,8 @@ class SparseU:
                     self._build_supertiles()
         if (self._ts_host is not None or self.strips_ts is not None) and ops.project_stream_ts_ok(movie2d, self.d2, mean):
             self._finish_ts(inv_std)
-            ops.project_stream_ts(movie2d, self.d2, self.strips_ts, self.bimg_ts, mean, z[: self.n_local], z[self.n_local :])
-            _submark("projection.stream")
+            ops.project_stream_ts(movie2d, self.d2, self.strips_ts, self.bimg_ts, mean, z[: self.n_local], z[self.n_local :],
+                                  mark=_submark)
             return
         if self._ts_host is not None or self.strips_ts is not None:   # unaligned movie: the older strip kernels
             if self._tc_host is None and self.strips_tc is None and self._regular is not None:

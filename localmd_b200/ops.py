@@ -1135,9 +1135,11 @@ def project_stream_ts_ok(movie2d, d2, mean):
     return ok and (mean is None or mean.data_ptr() % 16 == 0)
 
 
-def project_stream_ts(movie2d, d2, st_dev, bimg, mean, z_local, z_bg):
+def project_stream_ts(movie2d, d2, st_dev, bimg, mean, z_local, z_bg, mark=None):
     """K7 (TMA + tensor-memory operand): z_local[col, f] and z_bg[k, f] of U^T standardised movie in one streaming pass.
-    `bimg` must have been packed with the inv_std this projection is meant to apply (pack_strips_ts)."""
+    `bimg` must have been packed with the inv_std this projection is meant to apply (pack_strips_ts).
+    mark: optional callable(name) for CUDA-event marks: "projection.prep" is recorded right before the kernel launch (table
+    uploads, coefficient images and the zero fills lie before it), "projection.stream" right after it -- the kernel alone."""
     t, d = movie2d.shape
     assert z_local.dtype == torch.float32 and (z_local.numel() == 0 or z_local.stride(1) == 1)
     K = z_bg.shape[0]
@@ -1145,8 +1147,12 @@ def project_stream_ts(movie2d, d2, st_dev, bimg, mean, z_local, z_bg):
     zl = z_local if z_local.numel() else parts
     if st_dev["has_shared"] and z_local.numel():
         z_local[:, :t].zero_()   # blocks shared by two strips are accumulated by two atomic adds
+    if mark is not None:
+        mark("projection.prep")
     _call("pmd_project_stream_ts", _p(movie2d), movie_dtype_code(movie2d), t, d2, d, _p(st_dev["items"]), st_dev["n_items"],
           _p(st_dev["events"]), _p(bimg), st_dev["N"], _p(mean), _p(zl), zl.stride(0) if z_local.numel() else t, _p(parts), t,
           max(K, 1) * t, _stream())
+    if mark is not None:
+        mark("projection.stream")
     if K:
         z_bg[:, :t].copy_(parts[:, :K].sum(dim=0))

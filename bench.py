@@ -36,7 +36,7 @@ WORKLOADS = {
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -49,29 +49,73 @@ def parse():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clock / throttle-reason samples during the timed region."""
+    """SM clock / throttle-reason samples DURING the timed region.  In-process NVML (two light queries every 200 ms from a
+    daemon thread) when nvidia_ml_py is importable; otherwise one `nvidia-smi -lms` child.  The child's full query every
+    100 ms showed up as multi-millisecond outliers in single latency-bound stages of single steps (the final eigensolver's
+    ~300 dependent launches), so it is only the fallback."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index=0):
-        self.index, self.samples, self.proc = index, [], None
+        self.index, self.samples, self.proc, self.nvml, self._stop = index, [], None, None, threading.Event()
+        self.sm, self.reasons = [], set()
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def start(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "250"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        n = self.nvml
+        names = [("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)]
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                for name, bit in names:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
     def _read(self):
         for line in self.proc.stdout:
             self.samples.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=2)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
+                    "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -93,9 +137,10 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
+# ------------------------------------------------------------------------------------------------
 # The bounded sample of the workload that the CPU legs run (the oracle needs ~9 min for one full C2 pass on 16 cores):
 # same block size, same max_components / background rank / rank pruning, same init-window fraction t / T = 1/4 as C2,
 # on a 128x128 crop x 4096 frames.  Throughput is reported in FULL-FIELD-OF-VIEW frame equivalents:
@@ -314,6 +359,12 @@ def run_ours(args):
     if args.stage_times and rank == 0:
         sys.stderr.write("stage ms: %s\n" % json.dumps({k: round(v, 2) for k, v in stage.items() if isinstance(v, float)}))
         sys.stderr.write("n_cols/ranks info: %s\n" % json.dumps(stage.get("__info__", {})))
+    # the interpreter's cyclic collector off the timed region's critical path: everything allocated so far is frozen (never
+    # rescanned), so the collections that still trigger on the jobs' short-lived tensors stay short
+    import gc
+
+    gc.collect()
+    gc.freeze()
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:

@@ -237,7 +237,11 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
     extern __shared__ __align__(16) unsigned char jsm_raw[];
     using VT = typename JacVec<S>::type;
     constexpr int VW = JacVec<S>::W;
-    const S kTol = sizeof(S) == 8 ? (S)1e-15 : (S)3e-7;
+    // rotation threshold (relative to sqrt(a_pp a_qq)) and the early-exit bound: a sweep whose LARGEST rotated element was
+    // below kQuad leaves off-diagonal elements of second order (<= kQuad^2 < kTol), so the sweep that would only verify
+    // convergence is not run.  The eigenvectors are returned in float32 (6e-8), the float32 sweeps feed the sketch stage.
+    const S kTol = sizeof(S) == 8 ? (S)1e-14 : (S)1e-6;
+    const S kQuad = sizeof(S) == 8 ? (S)3e-8 : (S)3e-4;
     const int N = n + (n & 1);           // even size: index n (if any) is a padding row / column of zeros
     const int ld = N | 1;                // odd pitch of A
     const int ldv = (N + VW - 1) / VW * VW;
@@ -248,7 +252,7 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
     S* cc = Vt + (size_t)N * ldv;                               // [half]
     S* ss = cc + half;                                          // [half]
     int* pq = reinterpret_cast<int*>(ss + half);                // [half]: p | q << 8 | rotated << 16
-    __shared__ int n_rot;
+    __shared__ int n_rot, n_big;
     const int tid = threadIdx.x;
     const int64_t b = blockIdx.x;
     double* cb = cmat + b * (int64_t)n * n;
@@ -282,7 +286,7 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
     __syncthreads();
 
     for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-        if (tid == 0) n_rot = 0;
+        if (tid == 0) n_rot = n_big = 0;
         __syncthreads();
         for (int step = 0; step < N - 1; ++step) {
             if (tid < half) {
@@ -294,7 +298,9 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
                 int rot = 0;
                 if (q < n) {
                     const S apq = A[p * ld + q], app = A[p * ld + p], aqq = A[q * ld + q];
-                    if (apq != (S)0 && fabs(apq) > kTol * sqrt(fabs(app * aqq))) {
+                    const S scale = sqrt(fabs(app * aqq));
+                    if (apq != (S)0 && fabs(apq) > kTol * scale) {
+                        if (fabs(apq) > kQuad * scale) n_big = 1;     // (benign race: every writer stores 1)
                         const S tau = (aqq - app) / ((S)2 * apq);
                         const S t = (tau >= (S)0 ? (S)1 : (S)-1) / (fabs(tau) + sqrt((S)1 + tau * tau));
                         c = (S)1 / sqrt((S)1 + t * t);
@@ -352,7 +358,7 @@ jacobi_eigh_kernel(double* __restrict__ cmat, int n, int mode, int max_sweeps, d
             }
             __syncthreads();
         }
-        const int rots = n_rot;
+        const int rots = n_big ? n_rot : 0;
         __syncthreads();
 #ifdef PMD_TUNE
         if (tid == 0 && (rots == 0 || sweep == max_sweeps - 1)) atomicAdd(&g_jac_sweep_hist[sizeof(S) == 4][min(sweep + 1, 63)], 1ull);

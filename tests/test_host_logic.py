@@ -382,3 +382,24 @@ def test_utu_host_tables_match_numpy_formulation():
     np.testing.assert_array_equal(rowoff, ex - ex[first[b1]])
     width = np.bincount(b1, weights=r2, minlength=len(ranks)).astype(np.int64)
     np.testing.assert_array_equal(rowptr, np.concatenate([[0], np.cumsum(np.repeat(width, ranks))]))
+
+
+def test_sym_splits_fill_whole_waves():
+    """Split count of pmd_sym_product_f64: units = upper tiles x splits should fill whole waves of 148 SMs."""
+    from localmd_b200 import ops
+
+    s = ops.sym_splits(1650, 20000)            # 91 upper tiles: 13 splits -> 1183 units = 7.99 waves
+    assert s == 13 and 91 * s <= 8 * 148
+    assert ops.sym_splits(100, 500) == 1       # one tile, short inner dimension: no split
+    for n, k in [(330, 4096), (3860, 30000), (129, 100000)]:
+        s = ops.sym_splits(n, k)
+        assert 1 <= s <= 64 and (s == 1 or k // s >= 256)
+
+
+def test_block_orth_fits_matches_kernel_footprint():
+    """Shared-memory footprint of pmd_block_orth (csrc/orth.cu: block_orth_smem) as restated in ops.block_orth_fits."""
+    from localmd_b200 import ops
+
+    assert ops.block_orth_fits(400, 50) and ops.block_orth_fits(100, 60)
+    assert 2 * ((56 * 56 + 3 * 56) * 8 + 400 * 52 * 4 + 1024) <= 228 * 1024      # two 400 x 50 matrices per SM
+    assert not ops.block_orth_fits(1024, 50) and not ops.block_orth_fits(400, 65)

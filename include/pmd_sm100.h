@@ -394,6 +394,14 @@ int pmd_utu_pairs(const int32_t* pairs, int64_t n_pairs, const int64_t* pair_row
                   int64_t bh, int64_t bw, const int32_t* ranks, const int64_t* col0, const double* uvals64,
                   const int64_t* rowptr, double* vals, int32_t* cols, void* stream);
 
+/* Z_loc = (U_loc^T U_loc) X in float64 from the dense tiles written by pmd_utu_pairs, on the FP64 tensor cores: one CTA per
+ * (block b1, 256 columns of X) walks the pairs seg_ptr[b1] .. seg_ptr[b1 + 1] - 1 of the sorted pair list (seg_ptr [nb + 1]
+ * int32, host built from the block grid).  x [n_local][ldx], z [n_local][ldz] (rows of blocks with rank 0 do not exist).
+ * replaces: the products with u.T.dot(u) at decomposition.py:974-981 (local x local part). */
+int pmd_utu_apply_tiles(const int32_t* pairs, const int32_t* seg_ptr, int64_t nb, const int64_t* pair_rowoff,
+                        const int32_t* ranks, const int64_t* col0, const int64_t* rowptr, const double* vals,
+                        const double* x, int64_t ldx, int64_t m, double* z, int64_t ldz, void* stream);
+
 /* host-side tables of pmd_utu_pairs (no device work): pair_rowoff [n_pairs] and rowptr [sum(ranks) + 1] from the block
  * pairs (sorted by b1) and the kept ranks [nb].  Plain C++ so that the Python driver can run it on a worker thread
  * without holding the interpreter lock. */

@@ -613,6 +613,7 @@ class SparseU:
         self._ts_host = None
         self._ts_future = None
         self._utu_host = None
+        self._utu_tiles = None
         self._tables_started = False
         which = os.environ.get("PMD_K7", "ts")   # development switch between the generations of the projection kernel
         self._want_ts = bool(regular and which == "ts")
@@ -780,8 +781,10 @@ class SparseU:
                                      bg64)  # (n_cols, K)
             if self.n_local > 0:
                 host, self._utu_host = self._utu_host, None
-                csr = ops.utu_local_csr(self.starts, self.starts_dev, self.bh, self.bw, self.ranks_host, self.ranks_dev,
-                                        self.col0_host, self.col0_dev, self.uvals64, host=host)
+                rowptr, cols, vals, self._utu_tiles = ops.utu_local_csr(self.starts, self.starts_dev, self.bh, self.bw, self.ranks_host,
+                                                                         self.ranks_dev, self.col0_host, self.col0_dev, self.uvals64,
+                                                                         host=host)
+                csr = (rowptr, cols, vals)
             else:
                 csr = None
             self._gram = (csr, c)
@@ -797,8 +800,12 @@ class SparseU:
         if nl > 0:
             rowptr, cols, vals = csr
             r_loc = right64[:nl].contiguous()
-            rows = torch.arange(nl, dtype=torch.int32, device=right64.device)
-            z[:nl] = ops.reconstruct_f64(rowptr, cols, vals, r_loc, rows).t()
+            if getattr(self, "_utu_tiles", None) is not None and len(self.ranks_host) <= 65535:
+                # dense block-pair tiles on the FP64 tensor cores: the rows of `right` of a block are read once per pair
+                ops.utu_apply_tiles(self._utu_tiles, self.ranks_dev, self.col0_dev, rowptr, vals, r_loc, z[:nl])
+            else:
+                rows = torch.arange(nl, dtype=torch.int32, device=right64.device)
+                z[:nl] = ops.reconstruct_f64(rowptr, cols, vals, r_loc, rows).t()
             z[:nl] += torch.matmul(c[:nl], r_bg)
             z[nl:] = torch.matmul(c[:nl].t(), r_loc)
         else:

@@ -664,8 +664,9 @@ def utu_host_tables(starts_host, bh, bw, ranks_host):
 
 
 def utu_local_csr(starts_host, starts, bh, bw, ranks_host, ranks, col0_host, col0, uvals64, host=None):
-    """Canonical CSR (rowptr int64, cols int32, vals float64) of U_loc^T U_loc on the device.  host: the result of
-    utu_host_tables for the same arguments when it was computed ahead of time."""
+    """Canonical CSR (rowptr int64, cols int32, vals float64) of U_loc^T U_loc on the device, plus the tile tables
+    (pairs, seg_ptr, pair_rowoff) that utu_apply_tiles walks.  host: the result of utu_host_tables for the same
+    arguments when it was computed ahead of time."""
     _req(uvals64, torch.float64, "uvals64"), _req(ranks, torch.int32, "ranks"), _req(col0, torch.int64, "col0")
     dev = uvals64.device
     pairs, rowoff, rowptr = host if host is not None else utu_host_tables(starts_host, bh, bw, ranks_host)
@@ -673,38 +674,27 @@ def utu_local_csr(starts_host, starts, bh, bw, ranks_host, ranks, col0_host, col
     vals = torch.empty(nnz, dtype=torch.float64, device=dev)
     cols = torch.empty(nnz, dtype=torch.int32, device=dev)
     rowptr_d = h2d(rowptr, dev)
+    tiles = None
     if nnz:
         pairs_d = h2d(pairs, dev)  # named: the tensors must outlive the pointer extraction
         rowoff_d = h2d(rowoff, dev)
         _call("pmd_utu_pairs", _p(pairs_d), pairs.shape[0], _p(rowoff_d), _p(starts), bh, bw, _p(ranks), _p(col0), _p(uvals64),
               _p(rowptr_d), _p(vals), _p(cols), _stream())
-    return rowptr_d, cols, vals
+        seg = np.searchsorted(pairs[:, 0], np.arange(len(ranks_host) + 1), side="left").astype(np.int32)   # pairs are sorted by b1
+        tiles = (pairs_d, h2d(seg, dev), rowoff_d)
+    return rowptr_d, cols, vals, tiles
 
 
-
-def export_csr(uvals64, bg, d1, d2, row_starts, col_starts, bh, bw, ranks, col0, n_local, row_ids):
-    """Canonical CSR of U straight from the block-component form (pmd_export_csr; see header): returns
-    ((indptr_rel, cols_rel, vals_rel64), (indptr_phys, cols_phys, vals_phys32)) with the cols / vals buffers sized for the
-    worst case (every stored value nonzero); the true number of entries is indptr[-1] (the caller slices once it reads it)."""
-    _req(uvals64, torch.float64, "uvals64"), _req(bg, torch.float32, "bg"), _req(ranks, torch.int32, "ranks"), _req(col0, torch.int64, "col0")
-    dev = uvals64.device
-    d, K = d1 * d2, bg.shape[0]
-    rs, cs = row_starts, col_starts     # int32 device tensors (ascending block-row / block-column origins)
-    _req(rs, torch.int32, "row_starts"), _req(cs, torch.int32, "col_starts")
-    if row_ids is not None:
-        _req(row_ids, torch.int64, "row_ids")
-    counts = torch.empty((2, d), dtype=torch.int64, device=dev)
-    args = (_p(uvals64), _p(bg), K, d1, d2, _p(rs), rs.numel(), _p(cs), cs.numel(), bh, bw, _p(ranks), _p(col0), n_local, _p(row_ids))
-    _call("pmd_export_csr", *args, 0, _p(counts[0]), _p(counts[1]), None, None, None, None, None, None, _stream())
-    indptr = torch.zeros((2, d + 1), dtype=torch.int64, device=dev)
-    for i in range(2):   # two 1-D scans (the device-wide scan; a (2, d) scan along dim 1 runs as two single-CTA scans: 0.5 ms)
-        torch.cumsum(counts[i], dim=0, out=indptr[i, 1:])
-    nnz_max = n_local * bh * bw + K * d
-    cols = torch.empty((2, nnz_max), dtype=torch.int32, device=dev)
-    vals64 = torch.empty(nnz_max, dtype=torch.float64, device=dev)
-    vals32 = torch.empty(nnz_max, dtype=torch.float32, device=dev)
-    _call("pmd_export_csr", *args, 1, None, None, _p(indptr[0]), _p(indptr[1]), _p(cols[0]), _p(vals64), _p(cols[1]), _p(vals32), _stream())
-    return (indptr[0], cols[0], vals64), (indptr[1], cols[1], vals32)
+def utu_apply_tiles(tiles, ranks, col0, rowptr, vals, x, z):
+    """z[:n_local] = (U_loc^T U_loc) x in float64 from the dense block-pair tiles (pmd_utu_apply_tiles, FP64 tensor cores).
+    x (n_local, m), z (n_local, m): float64, rows contiguous."""
+    _req(vals, torch.float64, "vals"), _req(ranks, torch.int32, "ranks"), _req(col0, torch.int64, "col0")
+    if x.dtype != torch.float64 or z.dtype != torch.float64 or x.stride(1) != 1 or z.stride(1) != 1 or not x.is_cuda:
+        raise ValueError("x and z must be float64 CUDA tensors with contiguous rows")
+    pairs_d, seg_d, rowoff_d = tiles
+    _call("pmd_utu_apply_tiles", _p(pairs_d), _p(seg_d), ranks.numel(), _p(rowoff_d), _p(ranks), _p(col0), _p(rowptr), _p(vals),
+          _p(x), x.stride(0), x.shape[1], _p(z), z.stride(0), _stream())
+    return z
 
 
 def split_groups(rk):

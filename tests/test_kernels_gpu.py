@@ -492,9 +492,11 @@ def test_project_supertile(ops, bh, bw, max_rank, dtype, d1, d2):
         np.testing.assert_allclose(z2.cpu().numpy(), ref2, rtol=0, atol=2e-5 * np.abs(ref2).max())
 
 
-@pytest.mark.parametrize("bh,bw,d1,d2,max_rank", [(20, 20, 112, 95, 5), (10, 14, 33, 47, 3), (16, 16, 16, 16, 4), (12, 12, 50, 37, 7)])
-def test_utu_gram_times(ops, bh, bw, d1, d2, max_rank):
-    """Block-sparse U^T U (pmd_utu_pairs + pmd_project_cols_f64) applied to a dense right factor."""
+@pytest.mark.parametrize("bh,bw,d1,d2,max_rank,mcols", [(20, 20, 112, 95, 5, 9), (10, 14, 33, 47, 3, 9), (16, 16, 16, 16, 4, 9),
+                                                          (12, 12, 50, 37, 7, 9), (12, 12, 50, 37, 30, 70), (20, 20, 112, 95, 5, 300)])
+def test_utu_gram_times(ops, bh, bw, d1, d2, max_rank, mcols):
+    """Block-sparse U^T U (pmd_utu_pairs + pmd_utu_apply_tiles + pmd_project_cols_f64) applied to a dense right factor:
+    ranks above 24 (several row chunks per block), more than 256 columns (several column CTAs), ragged edges."""
     from localmd_b200.decomposition import SparseU
 
     rng = np.random.default_rng(bh + d1)
@@ -502,7 +504,7 @@ def test_utu_gram_times(ops, bh, bw, d1, d2, max_rank):
     starts, ranks, col0, uv, bg, U = _random_sparse_u(rng, d1, d2, bh, bw, max_rank, K)
     uv64 = uv.astype(np.float64)
     su = SparseU(starts, dev(starts), bh, bw, d1, d2, ranks.astype(np.int64), dev(ranks), dev(uv64), dev(uv), dev(bg))
-    right = rng.standard_normal((U.shape[1], 9))
+    right = rng.standard_normal((U.shape[1], mcols))
     got = su.utu_times_f64(dev(right)).cpu().numpy()
     ref = (U.T @ U) @ right
     np.testing.assert_allclose(got, ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max())

@@ -697,6 +697,31 @@ def utu_apply_tiles(tiles, ranks, col0, rowptr, vals, x, z):
     return z
 
 
+def export_csr(uvals64, bg, d1, d2, row_starts, col_starts, bh, bw, ranks, col0, n_local, row_ids):
+    """Canonical CSR of U straight from the block-component form (pmd_export_csr; see header): returns
+    ((indptr_rel, cols_rel, vals_rel64), (indptr_phys, cols_phys, vals_phys32)) with the cols / vals buffers sized for the
+    worst case (every stored value nonzero); the true number of entries is indptr[-1] (the caller slices once it reads it)."""
+    _req(uvals64, torch.float64, "uvals64"), _req(bg, torch.float32, "bg"), _req(ranks, torch.int32, "ranks"), _req(col0, torch.int64, "col0")
+    dev = uvals64.device
+    d, K = d1 * d2, bg.shape[0]
+    rs, cs = row_starts, col_starts     # int32 device tensors (ascending block-row / block-column origins)
+    _req(rs, torch.int32, "row_starts"), _req(cs, torch.int32, "col_starts")
+    if row_ids is not None:
+        _req(row_ids, torch.int64, "row_ids")
+    counts = torch.empty((2, d), dtype=torch.int64, device=dev)
+    args = (_p(uvals64), _p(bg), K, d1, d2, _p(rs), rs.numel(), _p(cs), cs.numel(), bh, bw, _p(ranks), _p(col0), n_local, _p(row_ids))
+    _call("pmd_export_csr", *args, 0, _p(counts[0]), _p(counts[1]), None, None, None, None, None, None, _stream())
+    indptr = torch.zeros((2, d + 1), dtype=torch.int64, device=dev)
+    for i in range(2):   # two 1-D scans (the device-wide scan; a (2, d) scan along dim 1 runs as two single-CTA scans: 0.5 ms)
+        torch.cumsum(counts[i], dim=0, out=indptr[i, 1:])
+    nnz_max = n_local * bh * bw + K * d
+    cols = torch.empty((2, nnz_max), dtype=torch.int32, device=dev)
+    vals64 = torch.empty(nnz_max, dtype=torch.float64, device=dev)
+    vals32 = torch.empty(nnz_max, dtype=torch.float32, device=dev)
+    _call("pmd_export_csr", *args, 1, None, None, _p(indptr[0]), _p(indptr[1]), _p(cols[0]), _p(vals64), _p(cols[1]), _p(vals32), _stream())
+    return (indptr[0], cols[0], vals64), (indptr[1], cols[1], vals32)
+
+
 def split_groups(rk):
     """Split `rk` kept components into ceil(rk/4) groups of nearly equal size (each <= 4)."""
     ng = (rk + 3) // 4

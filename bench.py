@@ -59,6 +59,7 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.samples, self.proc, self.nvml, self._stop = index, [], None, None, threading.Event()
+        self._go = threading.Event()     # set by begin(): sampling starts with the timed region, initialisation happens before it
         self.sm, self.reasons = [], set()
 
     def _physical_index(self):
@@ -95,6 +96,7 @@ class ClockSampler:
         n = self.nvml
         names = [("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
                  ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)]
+        self._go.wait()
         while not self._stop.is_set():
             try:
                 self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
@@ -106,6 +108,9 @@ class ClockSampler:
                 pass
             self._stop.wait(0.2)
 
+    def begin(self):
+        self._go.set()
+
     def _read(self):
         for line in self.proc.stdout:
             self.samples.append(line.strip())
@@ -113,6 +118,7 @@ class ClockSampler:
     def stop(self):
         if self.nvml is not None:
             self._stop.set()
+            self._go.set()
             self.thread.join(timeout=2)
             return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_sm,
                     "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml"}
@@ -365,14 +371,17 @@ def run_ours(args):
 
     gc.collect()
     gc.freeze()
-    barrier()
+    # the sampler starts BEFORE the barrier: NVML initialisation takes tens of milliseconds on rank 0, and a rank that enters
+    # the timed region late makes every other rank wait for it at the first collective (max over ranks = +10 ms per step at N = 2)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    barrier()
     n0 = ops.LAUNCHES["count"]
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     per_step = []
     ev0.record()
+    sampler.begin()
     for _ in range(args.steps):
         tms = {"__detail__": True}
         localmd_b200.localmd_decomposition(movie, timings=tms, **kw)

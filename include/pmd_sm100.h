@@ -74,7 +74,10 @@ int pmd_standardize_frames(const void* movie, int dtype, int64_t d, const int64_
 int pmd_gram_f64(const float* a, int64_t batch, int64_t n, int64_t m_len, int64_t batch_stride,
                  int64_t row_stride, int64_t inner_stride, double* c, void* stream);
 
-/* batched symmetric eigensolver (cyclic parallel Jacobi, float64, one CTA per matrix, n <= 112).
+/* batched symmetric eigensolver (cyclic parallel Jacobi in shared memory, one CTA per matrix, n <= 112; a step's disjoint
+ * rotations are applied as one pass over the 2 x 2 blocks of the upper triangle, the eigenvectors are kept transposed).
+ * Rotations are skipped below 1e-14 (float32 sweeps: 1e-6) of sqrt(a_pp a_qq); the sweeps stop after a sweep whose largest
+ * rotated element was below the second-order bound 3e-8 (3e-4) or that rotated nothing.
  * c: [batch][n][n] double (destroyed).  Outputs: w [batch][n] double eigenvalues, descending;
  * vecs [batch][n][n] float32, column j = eigenvector j, scaled per `mode`:
  *   0: orthonormal eigenvectors E
@@ -96,7 +99,7 @@ int pmd_standardize_frames_t(const void* movie, int dtype, int64_t d, const int6
                              const float* mean, const float* stdv, float* out, int64_t ld, void* stream);
 
 /* batched in-place orthonormalisation of the first n columns of x [batch][m][ldx] (float32), one CTA per matrix held
- * in shared memory (n <= 64):  if g_ext != NULL first  X <- X L_g^-T  with g_ext[b] = L_g L_g^T ([batch][n][n]
+ * in shared memory (n <= 64; Gram and triangular solve on the FP64 tensor cores, mma.sync m8n8k4):  if g_ext != NULL first  X <- X L_g^-T  with g_ext[b] = L_g L_g^T ([batch][n][n]
  * float64: used with the Gram of the temporal components so that X = block * V^T becomes block * (orthonormal
  * temporal basis)^T, decomposition.py:301-306); then `passes` rounds of CholQR (float64 Gram, in-kernel Cholesky,
  * triangular solve).  Numerically dependent columns are set to zero.

@@ -975,7 +975,18 @@ def projected_svd(projection, data, group=None, after_gram=None):
         right = ops.matmul_3xtf32_any(left.t(), data) / div[:, None]
         return ops.matmul_3xtf32_any(projection, left), sing, right
     if group is not None:
-        raise NotImplementedError("frame-sharded projected_svd needs k <= T")
+        # k > T (fewer frames than components: tiny movies).  The T x T Gram couples every pair of frames, so the local column
+        # blocks are exchanged (k x T floats, small by construction), every rank solves the same problem and keeps its own
+        # block of Vt.
+        rank, world = sharding.dist_info(group)
+        mine = torch.tensor([n], dtype=torch.int64, device=dev)
+        alln = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(alln, mine, group=group)
+        counts = [int(x.item()) for x in alln]
+        full = sharding.ragged_all_gather(data.t().contiguous(), counts, group).t().contiguous()   # (k, T)
+        rmix, sing, vt = projected_svd(projection, full)
+        off = sum(counts[:rank])
+        return rmix, sing, vt[:, off : off + n].contiguous()
     d64 = data.to(torch.float64)
     gram = torch.matmul(d64.t(), d64)
     gram = 0.5 * (gram + gram.t())

@@ -147,6 +147,16 @@ def _svd(rank, world):
     assert np.abs(a - b).max() < 1e-3 * np.abs(b).max()
     vt = sharding.ragged_all_gather(vt_sh.t().contiguous(), [h - l for l, h in bounds], dist.group.WORLD).t()
     np.testing.assert_allclose(np.abs((vt @ vt.t()).numpy() - np.eye(k)).max(), 0, atol=1e-3)
+    # fewer frames than components (k > T): the column blocks are exchanged and every rank solves the T x T problem
+    T2 = 120     # (above 112, where the small-matrix Jacobi kernel -- device only -- would take over)
+    data2 = rng.standard_normal((k, T2)).astype(np.float32)
+    lo2, hi2 = [(0, 47), (47, T2)][rank] if world == 2 else sharding.shard_bounds(T2, world)[rank]
+    r2s, s2s, vt2s = projected_svd(torch.from_numpy(proj), torch.from_numpy(data2[:, lo2:hi2].copy()), dist.group.WORLD)
+    r2f, s2f, vt2f = projected_svd(torch.from_numpy(proj), torch.from_numpy(data2))
+    assert tuple(vt2s.shape) == (T2, hi2 - lo2)
+    np.testing.assert_allclose(s2s.numpy(), s2f.numpy(), rtol=1e-6)
+    np.testing.assert_allclose(vt2s.numpy(), vt2f.numpy()[:, lo2:hi2], atol=1e-6)
+    np.testing.assert_allclose(r2s.numpy(), r2f.numpy(), rtol=1e-5, atol=1e-5)
 
 
 def test_sharded_projected_svd_gloo():

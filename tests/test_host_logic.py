@@ -403,3 +403,24 @@ def test_block_orth_fits_matches_kernel_footprint():
     assert ops.block_orth_fits(400, 50) and ops.block_orth_fits(100, 60)
     assert 2 * ((56 * 56 + 3 * 56) * 8 + 400 * 52 * 4 + 1024) <= 228 * 1024      # two 400 x 50 matrices per SM
     assert not ops.block_orth_fits(1024, 50) and not ops.block_orth_fits(400, 65)
+
+
+def test_jacobi_block_fold_enumerates_upper_triangle_once():
+    """Index arithmetic of jacobi_eigh_kernel (csrc/dense_small.cu): item m of the folded rectangle -> 2 x 2 block (k, l) with
+    k <= l; every block of the upper triangle of the (N/2) x (N/2) block grid must be produced exactly once."""
+    for half in range(1, 57):
+        fold_cols = half if half & 1 else half + 1
+        n_blocks = half * (half + 1) // 2
+        seen = set()
+        for m in range(n_blocks):
+            a, c = divmod(m, fold_cols)
+            if a + c < half:
+                k, l = a, a + c
+            elif half & 1:
+                k, l = half - a, c
+            else:
+                k = half - 1 - a
+                l = k + (c - (half - a))
+            assert 0 <= k <= l < half and (k, l) not in seen, (half, m, k, l)
+            seen.add((k, l))
+        assert len(seen) == n_blocks
